@@ -1,0 +1,152 @@
+/*
+ * nestfit_b200.h -- C ABI of the B200-native NestFit likelihood hot path.
+ *
+ * Plain C, pointers and sizes only; no torch / CUDA types in any signature
+ * (streams are passed as `void*` holding a cudaStream_t, 0 = default stream).
+ * Every entry point returns an int status: 0 = NF_OK, negative = NF_E*, positive
+ * = a cudaError_t.  No exceptions cross the boundary.  NaN parameters give NaN
+ * (or null-model) log-likelihoods exactly like the reference's `void` callbacks.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   - `Runner.c_loglikelihood(double *utheta, double *lnL)`  nestfit/core/core.pxd:72,
+ *     `AmmoniaRunner.c_loglikelihood`                        nestfit/models/ammonia.pyx:423-432
+ *       -> nf_prior_transform + nf_nh3_loglike (batched: B vectors per call)
+ *   - `amm_predict` / `AmmoniaRunner.predict`                nestfit/models/ammonia.pyx:364-366,437-447
+ *       -> nf_nh3_predict
+ *   - `gauss_predict` / `GaussianRunner.c_loglikelihood`     nestfit/models/gaussian.pyx:53-54,98-102
+ *       -> nf_gauss_predict / nf_gauss_loglike
+ *   - `AmmoniaSpectrum.__init__`, `Spectrum.__init__`        nestfit/models/ammonia.pyx:245-277, nestfit/core/core.pyx:488-520
+ *       -> nf_pixels_create (+ nf_pixels_null_lnz)
+ *   - `PriorTransformer.c_transform`                         nestfit/core/core.pyx:459-476
+ *       -> nf_priors_create + nf_prior_transform
+ *   - MultiNest `run(...)` + `LogLike`/`dumper` callbacks    nestfit/core/cmultinest.pxd:5-33,
+ *     `run_multinest`, `mn_dump`                             nestfit/core/core.pyx:627-823
+ *       -> nf_ns_* (batched lock-step nested sampling over a block of pixels)
+ *
+ * Layouts: parameter vectors are parameter-major / component-minor,
+ * `[p0c0,p0c1,..,p1c0,..]` (ammonia.pyx:337-343); NH3 order voff,trot,tex,ntot,
+ * sigm,orth; Gaussian order voff,sigm,peak (gaussian.pyx:27-30).
+ */
+#ifndef NESTFIT_B200_H
+#define NESTFIT_B200_H
+
+#include <stdint.h>
+#include "nf_priors.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NF_ABI_VERSION 1
+
+enum {
+    NF_OK = 0,
+    NF_EINVAL = -1,   /* bad argument (size, NULL, unsupported configuration) */
+    NF_ENOMEM = -2,   /* host allocation failed                               */
+    NF_ENODEV = -3    /* no usable CUDA device                                */
+};
+
+enum { NF_MODEL_NH3 = 1, NF_MODEL_GAUSS = 2 };
+enum { NF_F32 = 0, NF_F64 = 1 };
+/* flags of the NH3 model (ammonia.pyx:344-347) */
+enum { NF_FLAG_COLD = 1, NF_FLAG_LTE = 2 };
+
+#define NF_MAX_SPEC 6       /* spectra (transitions) scored together per pixel */
+#define NF_MAX_NCOMP_NH3 4  /* velocity components of the fused NH3 kernel      */
+#define NF_MAX_NCOMP_GAUSS 32
+
+typedef struct nf_pixels nf_pixels; /* opaque: a block of pixels resident in HBM */
+typedef struct nf_priors nf_priors; /* opaque: a prior plan resident in HBM      */
+typedef struct nf_sampler nf_sampler; /* opaque: batched nested-sampling state   */
+
+int nf_abi_version(void);
+const char *nf_error_string(int code);
+int nf_device_count(int *count);
+
+/* ---- pixel blocks ------------------------------------------------------- */
+/*
+ * Upload a block of `n_pix` pixels, each with `n_spec` spectra of `n_chan`
+ * channels on uniform ascending frequency axes x_j = nu_min[s] + j*nu_chan[s]
+ * (Spectrum.__init__, core.pyx:503-514).  `data` is host memory
+ * [n_pix][n_spec][n_chan] of `dtype` (NF_F32 / NF_F64), `noise` host
+ * [n_pix][n_spec] (one scalar rms per spectrum, core.pyx:507).
+ * model == NF_MODEL_NH3: `trans_id[s]` in 1..9 selects the (J,K) inversion
+ * transition (ammonia.pyx:245-271), `rest_freq` ignored.
+ * model == NF_MODEL_GAUSS: n_spec must be 1 and `rest_freq[0]` is the line rest
+ * frequency in Hz (gaussian.pyx:31-32).
+ * Data are stored as FP32 in HBM, channel-contiguous, rows padded to 32.
+ */
+int nf_pixels_create(int device, int model, int64_t n_pix, int n_spec, int n_chan,
+                     const double *nu_min, const double *nu_chan,
+                     const int *trans_id, const double *rest_freq,
+                     const void *data, int dtype, const double *noise,
+                     nf_pixels **out);
+/* Same, but `data_dev` (FP32 [n_pix][n_spec][n_chan]) and `noise_dev`
+ * (FP64 [n_pix][n_spec]) already live on `device`; they are copied. */
+int nf_pixels_create_from_device(int device, int model, int64_t n_pix, int n_spec,
+                                 int n_chan, const double *nu_min,
+                                 const double *nu_chan, const int *trans_id,
+                                 const double *rest_freq, const float *data_dev,
+                                 const double *noise_dev, nf_pixels **out);
+int nf_pixels_free(nf_pixels *px);
+/* null-model evidence per pixel, -sum_s sum_j d^2/(2 sigma_s^2)
+ * (core.pyx:518-520, ammonia.pyx:411-415) -> host double[n_pix]. */
+int nf_pixels_null_lnz(const nf_pixels *px, double *out_host);
+
+/* ---- likelihood / prediction: device-pointer entry points --------------- */
+/*
+ * Score B parameter vectors.  `params_dev` is [B][n_model*ncomp] of
+ * `param_dtype` in physical units.  Vector b belongs to pixel
+ * pix_of_vec_dev[b] (int32, device) or, when that is NULL, to pixel
+ * b / vecs_per_pix.  Vectors of one pixel should be contiguous (the pixel's
+ * spectra are then staged once per CTA in shared memory); any order is correct.
+ * `lnL_dev` receives B doubles:  -sum (d-m)^2 / (2 sigma^2)  (core.pyx:522-530).
+ * Asynchronous on `stream`.
+ */
+int nf_nh3_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,
+                   const int32_t *pix_of_vec_dev, int64_t vecs_per_pix, int64_t B,
+                   int ncomp, int flags, double *lnL_dev, void *stream);
+/* Model spectra only: pred_dev [B][n_spec][n_chan] FP32 (ammonia.pyx:437-447).
+ * `px` supplies the axes/transitions; its data are not read. */
+int nf_nh3_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
+                   int64_t B, int ncomp, int flags, float *pred_dev, void *stream);
+int nf_gauss_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,
+                     const int32_t *pix_of_vec_dev, int64_t vecs_per_pix, int64_t B,
+                     int ncomp, double *lnL_dev, void *stream);
+int nf_gauss_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
+                     int64_t B, int ncomp, float *pred_dev, void *stream);
+
+/* ---- host-buffer entry points (the call a reference-side binding makes) -- */
+/* params_host [B][ndim] of param_dtype, pix_of_vec_host may be NULL (then
+ * vecs_per_pix is used), lnL_host double[B].  Copies are pipelined with the
+ * kernel over internal streams; the call returns when lnL_host is complete. */
+int nf_nh3_loglike_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                        const int32_t *pix_of_vec_host, int64_t vecs_per_pix,
+                        int64_t B, int ncomp, int flags, double *lnL_host);
+int nf_gauss_loglike_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                          const int32_t *pix_of_vec_host, int64_t vecs_per_pix,
+                          int64_t B, int ncomp, double *lnL_host);
+int nf_nh3_predict_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                        int64_t B, int ncomp, int flags, float *pred_host);
+int nf_gauss_predict_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                          int64_t B, int ncomp, float *pred_host);
+
+/* ---- prior transform ---------------------------------------------------- */
+int nf_priors_create(int device, const nf_prior_desc *priors, int n_prior,
+                     const nf_dist_desc *dists, int n_dist, const double *tables,
+                     int64_t n_tables, int n_model, nf_priors **out);
+int nf_priors_free(nf_priors *pr);
+/* In place, unit cube -> physical: u_dev [B][n_model*ncomp] doubles. */
+int nf_prior_transform(const nf_priors *pr, double *u_dev, int64_t B, int ncomp,
+                       void *stream);
+int nf_prior_transform_host(const nf_priors *pr, double *u_host, int64_t B, int ncomp);
+
+/* ---- kernel timing helper (bench / roofline) ---------------------------- */
+/* Milliseconds the last *_host call spent in kernels only (CUDA events on the
+ * launching streams), and how many kernels it launched. */
+int nf_last_call_stats(double *kernel_ms, int64_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESTFIT_B200_H */

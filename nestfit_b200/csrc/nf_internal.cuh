@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libnestfit_b200.so.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nestfit_b200.h"
+
+// Physical constants as compiled into the reference
+// (includes/model_includes.pxi:27-36, nestfit/models/ammonia.pyx:15-18).
+#define NF_CKMS 299792.458
+#define NF_CCMS 29979245800.0
+#define NF_H 6.62607015e-27
+#define NF_KB 1.380649e-16
+#define NF_TCMB 2.72548
+#define NF_BROT 298192.92e6
+#define NF_CROT 186695.86e6
+#define NF_FWHM 2.3548200450309493
+
+#define NF_WARPS_PER_CTA 8
+#define NF_THREADS (NF_WARPS_PER_CTA * 32)
+#define NF_TILE_VECS 64          // parameter vectors per CTA tile
+#define NF_MAX_LINES 32          // hyperfine lines per (component, spectrum) <= warp width
+#define NF_IEM_SIZE 1000         // 1/(e^x-1) table, nestfit/models/hyperfine.pyx:12
+
+// Per-spectrum constants prepared on the host in FP64.
+struct NfSpecMeta {
+    double nu_min;      // x_0 [Hz]                       core.pyx:513
+    double nu_chan;     // x_1 - x_0 [Hz]                 core.pyx:503
+    double inv_chan;    // 1 / nu_chan
+    double nu0;         // rest frequency [Hz]
+    double fracterm;    // c^2 A / (8 pi nu0^2)           ammonia.pyx:358
+    double width_c;     // c_kms / (nu0 sqrt(2 pi))       ammonia.pyx:359 (divided by sigma on device)
+    double hnu_k;       // h nu0 / k_B                    ammonia.pyx:355
+    double T0_first;    // h x_0 / k_B                    hyperfine.pyx:106
+    double T0_last;     // h x_{N-1} / k_B
+    double tbg0, tbg1;  // 1/expm1(T0_j/Tcmb) ~= tbg0 + tbg1*j   ammonia.pyx:273-277
+    float t0a, t0b;     // T0_j = t0a + t0b*j
+    int line_off;       // first line in the global line tables
+    int nlines;         // hyperfine lines of this transition (<= NF_MAX_LINES)
+    int J;              // rotational level J (=K), 1..9
+    int para;           // para (K % 3 != 0) or ortho
+};
+
+struct nf_pixels {
+    int device;
+    int model;
+    int64_t n_pix;
+    int n_spec, n_chan, n_pad;      // n_pad: channels per row in HBM (multiple of 32)
+    float *data;                    // [n_pix][n_spec][n_pad]
+    double *inv2s2;                 // [n_pix][n_spec]  1/(2 sigma^2)
+    double *null_lnz;               // [n_pix]
+    NfSpecMeta spec[NF_MAX_SPEC];
+    // pipelined host-call resources
+    cudaStream_t streams[2];
+    void *stage_dev[2];
+    void *stage_host[2];
+    size_t stage_bytes;
+};
+
+struct nf_priors {
+    int device;
+    int n_prior, n_dist, n_model;
+    int max_stride;
+    int64_t n_tables;
+    nf_prior_desc *priors;   // device
+    nf_dist_desc *dists;     // device
+    double *tables;          // device
+    nf_prior_desc *h_priors; // host copies (validation)
+    nf_dist_desc *h_dists;
+};
+
+struct NfLikeArgs {
+    const float *data;          // may be NULL (predict only)
+    const double *inv2s2;
+    const void *params;
+    const int32_t *pix_of_vec;  // may be NULL
+    int64_t vecs_per_pix;
+    int64_t B;
+    int64_t pix_stride;         // floats per pixel = n_spec * n_pad
+    double *lnL;                // may be NULL
+    float *pred;                // may be NULL: [B][n_spec][n_chan]
+    int param_f64;
+    int ncomp, n_spec, n_chan, n_pad;
+    int cold, lte;
+    int need_para, need_ortho;
+    NfSpecMeta spec[NF_MAX_SPEC];
+};
+
+// launchers (nf_model.cu)
+cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st);
+cudaError_t nf_launch_gauss(const NfLikeArgs &a, cudaStream_t st);
+cudaError_t nf_model_init_device_tables(int device);
+cudaError_t nf_launch_null_lnz(const float *data, const double *inv2s2, double *out,
+                               int64_t n_pix, int n_spec, int n_chan, int n_pad,
+                               cudaStream_t st);
+cudaError_t nf_launch_pack_rows(const void *src, int src_f64, float *dst, int64_t rows,
+                                int n_chan, int n_pad, cudaStream_t st);
+// nf_priors.cu
+cudaError_t nf_launch_prior_transform(const nf_priors *pr, double *u, int64_t B, int ncomp,
+                                      cudaStream_t st);
+
+extern thread_local double g_nf_last_kernel_ms;
+extern thread_local int64_t g_nf_last_launches;
