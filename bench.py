@@ -1,0 +1,479 @@
+#!/usr/bin/env python3
+"""
+bench.py -- NH3 log-likelihood throughput (BASELINE.json metric, config 2).
+
+Workload at every N: per GPU, 2^20 parameter vectors (3 velocity components,
+18 parameters) scored against 1024 synthetic pixels (2 x 1000 channels, NH3
+(1,1)+(2,2), 1024 vectors per pixel); one *step* = one pass of the fused
+likelihood kernel over that batch.  `value` = evals/s with inputs resident in
+HBM (CUDA-event timed), `e2e` = the same batch through the host-buffer C-ABI
+call (H2D of the parameters and D2H of lnL inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the reference's own CPU implementation of the same path
+(oracle/_ref = the unmodified reference compiled by oracle/build_ref.py; the C
+oracle port if that is absent) on all host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+NCOMP = 3
+N_PIX = int(os.environ.get("NF_BENCH_NPIX", "1024"))   # profiling runs shrink the batch; the bench uses 1024
+VPP = 1024
+N_CHAN = 1000
+DV = 0.07
+NOISE = 0.1
+B_TOTAL = N_PIX * VPP
+N_SETUP_SFU = 40 * 2 * NCOMP      # n_su = 40 * N_spec * ncomp
+WORKLOAD = "nh3_loglike_microbench: 2^20 vectors x 3 comp, 1024 px x 1024 vec, 2x1000 ch (configs[1])"
+
+
+# --------------------------------------------------------------------------
+# CPU reference / oracle workers (checker + baseline only)
+# --------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(kind, xs, data, noise):
+    _W["kind"] = kind
+    _W["xs"], _W["data"], _W["noise"] = xs, data, noise
+    if kind == "reference":
+        from oracle import ref
+        m = ref.load()
+        _W["amm"] = m.ammonia
+        _W["specs"] = {}
+    else:
+        from oracle import oracle as orc
+        _W["orc"] = orc
+
+
+def _worker_run(job):
+    params, pix = job
+    t0 = time.perf_counter()
+    if _W["kind"] == "reference":
+        amm = _W["amm"]
+        out = np.empty(params.shape[0])
+        for b in range(params.shape[0]):
+            p = int(pix[b])
+            specs = _W["specs"].get(p)
+            if specs is None:
+                specs = [amm.AmmoniaSpectrum(_W["xs"][t], _W["data"][p, t].copy(), float(_W["noise"][p, t]),
+                                             trans_id=t + 1) for t in (0, 1)]
+                _W["specs"] = {p: specs}      # keep one pixel's objects alive
+            v = params[b].copy()
+            lnl = 0.0
+            for s in specs:
+                amm.amm_predict(s, v)
+                lnl += s.loglikelihood
+            out[b] = lnl
+    else:
+        out = _W["orc"].nh3_batch(_W["xs"], [1, 2], params, NCOMP, data=_W["data"], noise=_W["noise"],
+                                  pix_of_vec=pix)["lnL"]
+    return out, time.perf_counter() - t0
+
+
+class CpuArm:
+    """All-core fan-out of the reference CPU path over a sample of vectors."""
+
+    def __init__(self, xs, data, noise):
+        from oracle import ref
+        self.kind = "reference" if ref.available() else "port"
+        self.cores = os.cpu_count() or 1
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_worker_init,
+                             initargs=(self.kind, xs, np.asarray(data, dtype=np.float64),
+                                       np.asarray(noise, dtype=np.float64)))
+
+    def run(self, params, pix):
+        """Score the vectors on all cores; returns (lnL, wall seconds)."""
+        n = params.shape[0]
+        nj = min(n, self.cores * 4)
+        bounds = np.linspace(0, n, nj + 1).astype(int)
+        jobs = [(params[a:b], pix[a:b]) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        t0 = time.perf_counter()
+        res = self.pool.map(_worker_run, jobs)
+        wall = time.perf_counter() - t0
+        return np.concatenate([r[0] for r in res]), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def axes():
+    from oracle import oracle as orc   # axis helper only (numpy arithmetic)
+    return [orc.bench_axis(1, N_CHAN, DV), orc.bench_axis(2, N_CHAN, DV)]
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def build_problem(nb, rank):
+    """Synthetic config-2 problem built with the product's own kernels."""
+    ut = nb.get_irdc_priors()
+    xs = axes()
+    rng = np.random.default_rng(1234)
+    # truth per pixel: ncomp_true in {1,2,3} cyclic, drawn through the prior; the model spectra
+    # come from the predict kernel (1-, 2-, 3-component launches), plus N(0, sigma^2) noise
+    clean = np.zeros((N_PIX, 2, N_CHAN), dtype=np.float32)
+    scratch = nb.PixelBlock("ammonia", xs, np.zeros((1, 2, N_CHAN), dtype=np.float32), NOISE, trans_ids=[1, 2])
+    for nc in (1, 2, 3):
+        idx = np.arange(nc - 1, N_PIX, 3)
+        U = rng.uniform(size=(idx.size * 2, 6 * nc))
+        T = ut.transform_batch(U, nc)
+        T = T[np.isfinite(T).all(axis=1)][:idx.size]
+        clean[idx] = scratch.predict(T, nc)
+    scratch.close()
+    data = clean + rng.normal(0.0, NOISE, size=clean.shape).astype(np.float32)
+    noise = np.full((N_PIX, 2), NOISE)
+    U = np.random.default_rng(4321 + rank).uniform(size=(B_TOTAL, 6 * NCOMP))
+    P = ut.transform_batch(U, NCOMP)
+    bad = ~np.isfinite(P).all(axis=1)
+    if bad.any():       # redraw non-finite rows
+        good = np.flatnonzero(~bad)
+        P[bad] = P[good[: bad.sum()]]
+    return xs, data, noise, P.astype(np.float32)
+
+
+def run_ours(args):
+    import torch
+    import nestfit_b200 as nb
+    from nestfit_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    dev = local_rank
+
+    xs, data, noise, P32 = build_problem(_with_device(nb, dev), rank)
+    blk = nb.PixelBlock("ammonia", xs, data, noise, trans_ids=[1, 2], device=dev)
+    d_params = torch.from_numpy(P32).to(f"cuda:{dev}")
+    d_lnl = torch.empty(B_TOTAL, dtype=torch.float64, device=f"cuda:{dev}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")   # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        _lib.check(lib.nf_nh3_loglike(blk.handle, d_params.data_ptr(), _lib.NF_F32, None, VPP, B_TOTAL, NCOMP, 0,
+                                      d_lnl.data_ptr(), stream), "nf_nh3_loglike")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        launch()
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                     # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        launch()
+        ev[k][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    lnl_dev = d_lnl.cpu().numpy()
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
+    h_params = torch.from_numpy(P32).pin_memory()
+    h_lnl = torch.empty(B_TOTAL, dtype=torch.float64).pin_memory()
+    hp, hl = h_params.numpy(), h_lnl.numpy()
+
+    def e2e_call():
+        _lib.check(lib.nf_nh3_loglike_host(blk.handle, _lib.ptr(hp), _lib.NF_F32, None, VPP, B_TOTAL, NCOMP, 0,
+                                           _lib.ptr(hl)), "nf_nh3_loglike_host")
+
+    for _ in range(2):
+        e2e_call()
+    n_e2e = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_call()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.allclose(hl, lnl_dev, rtol=1e-12, atol=1e-9), "host-call and device-call results differ"
+
+    times = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(times[0]), float(times[1])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    evals = float(B_TOTAL) * world
+    value = evals * args.steps / (total_ms * 1e-3)
+    e2e_value = evals * n_e2e / e2e_s
+
+    # ---- roofline of the dominant (only) kernel --------------------------------
+    from oracle import oracle as orc        # work accounting by the reference's window rule, FP64, on the host
+    ns = 8192
+    pick = np.random.default_rng(7).choice(B_TOTAL, size=ns, replace=False)
+    cnt = orc.nh3_batch(xs, [1, 2], P32[pick].astype(np.float64), NCOMP, count=True)["counters"] / float(ns)
+    n_g, n_rt = float(cnt[0]), float(cnt[1])
+    sfu_per_eval = n_g + n_rt + N_SETUP_SFU
+    flop_per_eval = 5 * n_g + 8 * n_rt + 3 * 2 * N_CHAN + 30 * NCOMP * (18 + 21)
+    mufu = _lib.C.c_double()
+    ffma = _lib.C.c_double()
+    _lib.check(lib.nf_measure_peaks(dev, _lib.C.byref(mufu), _lib.C.byref(ffma)), "nf_measure_peaks")
+    launch_s = (total_ms * 1e-3) / args.steps
+    ach_sfu = B_TOTAL * sfu_per_eval / launch_s * 1e-9          # Gop/s, one GPU
+    ach_fp32 = B_TOTAL * flop_per_eval / launch_s * 1e-9
+    bound = "sfu" if sfu_per_eval / mufu.value >= flop_per_eval / ffma.value else "fp32"
+    peak = mufu.value if bound == "sfu" else ffma.value
+    ach = ach_sfu if bound == "sfu" else ach_fp32
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("nf_like_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": bound, "achieved": ach, "peak": peak, "unit": "Gop/s" if bound == "sfu" else "GFLOP/s",
+        "frac": ach / peak, "traffic": traffic,
+        "peak_source": "measured live by nf_measure_peaks (MUFU.EX2 / FFMA register loops, this box)",
+        "work_per_eval": {"n_gauss": n_g, "n_rt": n_rt, "n_setup": N_SETUP_SFU, "sfu_ops": sfu_per_eval,
+                          "fp32_flop": flop_per_eval, "counted_on": f"{ns}-vector host sample (oracle, FP64 window rule)"},
+        "fp32": {"achieved_gflops": ach_fp32, "peak_gflops": ffma.value, "frac": ach_fp32 / ffma.value},
+        "hbm": {"algorithmic_bytes_per_launch": B_TOTAL * (4 * 6 * NCOMP + 8) + N_PIX * 2 * 1024 * 4,
+                "note": "80 B per eval + 8 KB per pixel staged once per CTA tile; not the bound"},
+    }
+
+    line = {
+        "metric": "NH3 loglike evals/s (3-comp, 2x1000 ch)", "value": value, "unit": "evals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 set-up and lnL accumulation)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "vectors_per_gpu": B_TOTAL, "pixels_per_gpu": N_PIX, "ncomp": NCOMP,
+                   "n_chan": [N_CHAN, N_CHAN], "l2": "flushed between timed iterations (256 MB memset)",
+                   "parallelism": f"replicated pixels, disjoint vector batches x{world}"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(P32.nbytes),
+                "d2h_bytes_per_step": int(B_TOTAL * 8), "steps": n_e2e,
+                "api": "nf_nh3_loglike_host (pinned host buffers, 2-stream pipelined chunks)"},
+        "gpu_launches": args.steps,
+        "roofline": roofline,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------
+    if world == 1 and not args.no_cpu:
+        arm = CpuArm(xs, data, noise)
+        pilot_n = 64 * arm.cores
+        pix_all = (np.arange(B_TOTAL) // VPP).astype(np.int32)
+        _, w = arm.run(P32[:pilot_n].astype(np.float64), pix_all[:pilot_n])
+        rate = pilot_n / w
+        n_s = int(min(B_TOTAL, max(pilot_n, rate * 12.0)))
+        n_s = (n_s // VPP) * VPP or VPP
+        lnl_cpu, w = arm.run(P32[:n_s].astype(np.float64), pix_all[:n_s])
+        arm.close()
+        err = np.abs(lnl_cpu - lnl_dev[:n_s])
+        line["cpu_baseline"] = {
+            "value": n_s / w, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
+            "sample": f"first {n_s} vectors of the same batch ({n_s // VPP} pixels), fork pool over all cores",
+            "max_abs_dlnL_vs_gpu": float(err.max()),
+            "parity_ok": bool((err <= 1e-3 + 2e-6 * np.abs(lnl_cpu)).all()),
+        }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _with_device(nb, dev):
+    """PixelBlock / PriorTransformer helpers default to device 0; bind to `dev`."""
+    if dev == 0:
+        return nb
+
+    class _NB:
+        pass
+    o = _NB()
+    o.get_irdc_priors = lambda: _DevPriors(nb.get_irdc_priors(), dev)
+    o.PixelBlock = lambda *a, **k: nb.PixelBlock(*a, **{**k, "device": dev})
+    return o
+
+
+class _DevPriors:
+    def __init__(self, ut, dev):
+        self.ut, self.dev = ut, dev
+
+    def transform_batch(self, u, ncomp):
+        return self.ut.transform_batch(u, ncomp, device=self.dev)
+
+
+# --------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import ref
+    from oracle import oracle as orc
+    xs = axes()
+    rng = np.random.default_rng(1234)
+    n_pix = 64                                   # bounded sample of the workload's pixels
+    if ref.available():
+        m = ref.load()
+        ut = ref.make_irdc_priors(m.core)
+
+        def transform(U, nc):
+            P = U.copy()
+            for row in P:
+                ut.transform(row, nc)
+            return P
+    else:
+        import nestfit_b200.prior_constructors as pc
+        packed = pc.get_irdc_priors().pack()
+
+        def transform(U, nc):
+            return orc.prior_transform(packed, U, nc)
+    clean = np.zeros((n_pix, 2, N_CHAN))
+    for nc in (1, 2, 3):
+        idx = np.arange(nc - 1, n_pix, 3)
+        T = transform(rng.uniform(size=(idx.size * 2, 6 * nc)), nc)
+        T = T[np.isfinite(T).all(axis=1)][:idx.size]
+        clean[idx] = orc.nh3_batch(xs, [1, 2], T, nc, want_pred=True)["pred"]
+    data = (clean + rng.normal(0.0, NOISE, size=clean.shape)).astype(np.float32).astype(np.float64)
+    noise = np.full((n_pix, 2), NOISE)
+    arm = CpuArm(xs, data, noise)
+    # per-step sample sized from a pilot so K + W steps finish within a few minutes
+    pilot = 32 * arm.cores
+    Ppil = transform(np.random.default_rng(4321).uniform(size=(pilot * 2, 6 * NCOMP)), NCOMP)
+    Ppil = Ppil[np.isfinite(Ppil).all(axis=1)][:pilot].astype(np.float32).astype(np.float64)
+    _, w = arm.run(Ppil, (np.arange(pilot) % n_pix).astype(np.int32))
+    rate = pilot / w
+    budget_s = 150.0 / float(args.steps + max(args.warmup, 1))
+    n_s = int(max(pilot, min(rate * min(budget_s, 15.0), 1 << 18)))
+    n_s = max(n_pix, (n_s // n_pix) * n_pix)
+    U = np.random.default_rng(4321).uniform(size=(int(n_s * 1.05) + 64, 6 * NCOMP))
+    P = transform(U, NCOMP)
+    P = P[np.isfinite(P).all(axis=1)][:n_s].astype(np.float32).astype(np.float64)
+    pix = np.sort(np.arange(P.shape[0]) % n_pix).astype(np.int32)
+    for _ in range(max(args.warmup, 1)):
+        arm.run(P, pix)
+    t_tot = 0.0
+    for _ in range(args.steps):
+        _, w = arm.run(P, pix)
+        t_tot += w
+    arm.close()
+    value = P.shape[0] * args.steps / t_tot
+    sample = f"{P.shape[0]} vectors per step over {n_pix} pixels (bounded sample of the 2^20-vector batch)"
+    line = {
+        "impl": "reference", "metric": "NH3 loglike evals/s (3-comp, 2x1000 ch)", "value": value,
+        "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "ncomp": NCOMP, "n_chan": [N_CHAN, N_CHAN], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch one process per GPU (the driver does this itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

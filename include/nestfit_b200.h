@@ -146,6 +146,10 @@ int nf_prior_transform_host(const nf_priors *pr, double *u_host, int64_t B, int 
  * launching streams), and how many kernels it launched. */
 int nf_last_call_stats(double *kernel_ms, int64_t *n_launches);
 
+/* Measured roofline denominators on `device`: MUFU.EX2 results per second
+ * (Gop/s) and FP32 FMA rate (GFLOP/s, 2 flop per FMA), register-resident loops. */
+int nf_measure_peaks(int device, double *mufu_gops, double *ffma_gflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "nf_prior_transform": ([_VP, _VP, _I64, _I, _VP], _I),
     "nf_prior_transform_host": ([_VP, _VP, _I64, _I], _I),
     "nf_last_call_stats": ([_PD, C.POINTER(_I64)], _I),
+    "nf_measure_peaks": ([_I, _PD, _PD], _I),
 }
 
 

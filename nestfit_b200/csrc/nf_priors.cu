@@ -59,9 +59,11 @@ __device__ __forceinline__ double pow_int(double x, int s)
 __device__ double placement_draw(const DistView &v, double x_lo, double x_hi, int sfact, double u)
 {
     const int size = v.size;
-    if (!(x_lo == x_lo) || !(x_hi == x_hi) || !(u == u)) return nan("");
+    if (!(u == u)) return nan("");
     if (x_lo > x_hi) { double t = x_lo; x_lo = x_hi; x_hi = t; }
     double r_lo = (x_lo - v.xmin) / v.dx, r_hi = (x_hi - v.xmin) / v.dx;
+    // A NaN bound (a previous component's degenerate draw) converts to the most negative
+    // integer in the reference's C cast on x86 and is then clamped; fmax(NaN, x) = x.
     r_lo = fmin(fmax(r_lo, -1.0e9), 1.0e9);
     r_hi = fmin(fmax(r_hi, -1.0e9), 1.0e9);
     int i_lo = (int)r_lo, i_hi = (int)r_hi;          // C truncation

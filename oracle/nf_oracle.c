@@ -332,15 +332,23 @@ static double cdf_interp(const dist_view *v, double u)
     return 1.0 / slope * (u - v->cdf[i_lo]) + v->xax[i_lo];
 }
 
+static long cast_long(double r)
+{
+    if (!(r == r) || r >= 9.0e18 || r <= -9.0e18) return (-9223372036854775807L - 1L);
+    return (long)r;
+}
+
 /* Distribution.cdf_over_interval, core.pyx:109-161 */
 static void cdf_over_interval(dist_view *v, double x_lo, double x_hi, double sfact)
 {
     long size = v->d->size, i, i_lo, i_hi;
     double csum = 0.0, inv_delta_i, scale;
     if (x_lo > x_hi) { double t = x_lo; x_lo = x_hi; x_hi = t; }
-    i_lo = (long)((x_lo - v->d->xmin) / v->d->dx);
+    /* (long)NaN is undefined in C; the reference binary (x86-64 cvttsd2si) yields
+     * LONG_MIN, made explicit here.  NaN bounds arise after a degenerate draw. */
+    i_lo = cast_long((x_lo - v->d->xmin) / v->d->dx);
     if (i_lo >= size) i_lo = size - 1; else if (i_lo < 0) i_lo = 0;
-    i_hi = (long)((x_hi - v->d->xmin) / v->d->dx);
+    i_hi = cast_long((x_hi - v->d->xmin) / v->d->dx);
     if (i_hi == i_lo) i_hi = i_lo + 1;
     if (i_hi > size) i_hi = size; else if (i_hi < 0) i_hi = 1;
     for (i = 0; i < i_lo; i++) v->cdf[i] = 0.0;
