@@ -9,7 +9,9 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libnestfit_b200.so"
+import os as _os
+# NESTFIT_B200_LIB lets kernel experiments load an alternative build of the same ABI
+LIB_PATH = Path(_os.environ.get("NESTFIT_B200_LIB", _PKG / "libnestfit_b200.so"))
 
 NF_MODEL_NH3, NF_MODEL_GAUSS = 1, 2
 NF_F32, NF_F64 = 0, 1

@@ -25,6 +25,9 @@
 #include "../../include/nf_nh3_tables.h"
 
 #define NF_FULL 0xffffffffu
+#ifndef NF_MIN_CTAS
+#define NF_MIN_CTAS 3
+#endif
 #define NF_LOG2E 1.4426950408889634
 #define NF_HK (NF_H / NF_KB)
 
@@ -149,19 +152,76 @@ __device__ __forceinline__ double ld_param(const void *base, int64_t idx)
     return (double)__ldg(reinterpret_cast<const T *>(base) + idx);
 }
 
+// One hyperfine line of one (component, spectrum): 32 bytes, read with one LDS.128 + one LDS.64.
+struct __align__(32) LineRec {
+    float4 a;   // {R, -k2, 2*k2*phi, weight * 2^(-k2*phi^2)}
+    float2 w;   // {lo - R, hi - R}: window [lo, hi) in the line's own integer frame
+    float2 pad;
+};
+
 // Per-warp scratch in shared memory.
 template <int NC>
 struct __align__(16) WarpScratch {
-    float4 lineA[NC][NF_MAX_LINES];        // {R, -k2, 2*k2*phi, -k2*phi^2}
-    float4 lineB[NC][NF_MAX_LINES];        // {tau weight, lo - R, hi - R, 0}
+    LineRec line[NC][NF_MAX_LINES];
     float4 amp[NC][NF_MAX_SPEC];           // {aL, bL, aR, bR} of T_B amplitude lines
     double tauT[NC][NF_MAX_SPEC];          // main-line optical depth
     double soc[NC], voc[NC];               // sigma / c_kms, voff / c_kms
 };
 
+__device__ __forceinline__ float warp_sum_f32(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NF_FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// tau += w * e  for lanes whose channel lies inside the line's window [dlo, dhi)
+__device__ __forceinline__ void masked_fma(float &tau, float w, float e, float d0, float dlo, float dhi)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.ge.f32 p, %1, %2;\n"
+        "setp.lt.and.f32 p, %1, %3, p;\n"
+        "@p fma.rn.f32 %0, %4, %5, %0;\n"
+        "}\n"
+        : "+f"(tau)
+        : "f"(d0), "f"(dlo), "f"(dhi), "f"(w), "f"(e));
+}
+
+// One windowed Gaussian term of line record (A, Bw) at channel coordinate xj.
+__device__ __forceinline__ void line_term(float &tau, const LineRec *rec, float xj)
+{
+    const float4 A = rec->a;
+    const float2 Bw = rec->w;
+    const float d0 = xj - A.x;                 // exact: integer-valued floats
+    const float t = fmaf(A.y, d0, A.z);
+    const float e = ex2_approx(t * d0);        // 2^(-k2 (d0^2 - 2 phi d0)); 2^(-k2 phi^2) is in A.w
+    masked_fma(tau, A.w, e, d0, Bw.x, Bw.y);
+}
+
+// (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels J >= 3 and J = 0)
+#define NF_BK_F ((float)(NF_HK * NF_BROT))
+#define NF_CK_F ((float)(NF_HK * (NF_CROT - NF_BROT)))
+
+__device__ __forceinline__ float level_f32(int J, float inv_trot)
+{
+    const float Jf = (float)J;
+    const float x = (NF_BK_F * Jf * (Jf + 1.0f) + NF_CK_F * Jf * Jf) * inv_trot;
+    return x < 32.0f ? (2.0f * Jf + 1.0f) * ex2_approx(-(float)NF_LOG2E * x) : 0.0f;
+}
+
 // ---- the fused kernel -----------------------------------------------------
+// WRITE_PRED = false: log-likelihood against the pixel's data (a.data, a.lnL);
+// WRITE_PRED = true : model spectra only (a.pred), no data are read.
 template <int NC, bool IS_NH3, bool WRITE_PRED, typename PT>
-__global__ void __launch_bounds__(NF_THREADS)
+__global__ void __launch_bounds__(NF_THREADS, NF_MIN_CTAS)
 nf_like_kernel(const __grid_constant__ NfLikeArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -175,7 +235,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     WarpScratch<NC> &sc = scr_all[warp];
 
     const int64_t b0 = (int64_t)blockIdx.x * NF_TILE_VECS;
-    const bool have_data = a.data != nullptr;
+    constexpr bool have_data = !WRITE_PRED;
     int64_t pix0 = 0;
     if (have_data) {
         pix0 = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b0) : b0 / a.vecs_per_pix;
@@ -189,7 +249,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     const int ncomp = IS_NH3 ? NC : a.ncomp;   // NH3: template; Gaussian: lines of one group
     const int ndim = IS_NH3 ? 6 * NC : 3 * a.ncomp;
     const int nchunks = (a.n_chan + 31) >> 5;
-    const float xl = (float)lane;
+    const uint32_t sdata_addr = smem_u32(sdata) + (uint32_t)lane * 4u;
 
     for (int64_t b = b0 + warp; b < b0 + NF_TILE_VECS && b < a.B; b += NF_WARPS_PER_CTA) {
         const int64_t pbase = b * ndim;
@@ -197,36 +257,35 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
         if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;
 
         if (IS_NH3) {
-            // ---- P1: partition function, lanes <-> J (ammonia.pyx:289-315) ----
-            double zlev = 0.0, qtot = 1.0, trot_mine = 1.0;
+            // ---- P1: partition sums over J, lanes <-> J (ammonia.pyx:289-315).  Levels
+            // J = 1, 2 (which carry all but ~1e-3 of Q_para) are added in FP64 in P2; the
+            // rest go through MUFU.EX2 in FP32. ----
+            float q32 = 0.0f;
+            double trot_mine = 1.0;
             const int my_c = lane / a.n_spec, my_s = lane - my_c * a.n_spec;
             const bool pair_lane = lane < NC * a.n_spec;
-            const int my_J = pair_lane ? a.spec[my_s].J : 0;
+            const int my_J = pair_lane ? a.spec[my_s].J : 1;
             const int my_para = pair_lane ? a.spec[my_s].para : 1;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 double trot = ld_param<PT>(a.params, pbase + 1 * NC + c);
                 if (a.cold)  // swift_convert, ammonia.pyx:280-286
                     trot = trot / (1.0 + (trot / 41.18) * log(1.0 + 0.6 * exp(-15.7 / trot)));
-                const double J = (double)lane;
-                double aJ = NF_HK * (NF_BROT * J * (J + 1.0) + (NF_CROT - NF_BROT) * J * J);
-                double lev = (2.0 * J + 1.0) * fastexp_f64(aJ / trot);
-                double qp = (lane % 3 != 0) ? lev : 0.0;
-                double qo = (lane % 3 == 0) ? 2.0 * lev : 0.0;
-                if (!(trot < 299.0)) {  // levels J >= 32 underflow FastExp's range below ~301 K
-                    const double J2 = (double)(lane + 32);
+                const float itr = 1.0f / (float)trot;
+                float lev = (lane == 1 || lane == 2) ? 0.0f : level_f32(lane, itr);
+                float qp = (lane % 3 != 0) ? lev : 0.0f;
+                float qo = (lane % 3 == 0) ? 2.0f * lev : 0.0f;
+                if (!(trot < 299.0)) {  // levels J >= 32 are zero in FastExp's range below ~301 K
                     if (lane + 32 <= 50) {
-                        double a2 = NF_HK * (NF_BROT * J2 * (J2 + 1.0) + (NF_CROT - NF_BROT) * J2 * J2);
-                        double l2 = (2.0 * J2 + 1.0) * fastexp_f64(a2 / trot);
-                        if ((lane + 32) % 3 != 0) qp += l2; else qo += 2.0 * l2;
+                        const float l2 = level_f32(lane + 32, itr);
+                        if ((lane + 32) % 3 != 0) qp += l2; else qo += 2.0f * l2;
                     }
                 }
-                double zl = __shfl_sync(NF_FULL, lev, my_J);
-                if (a.need_para) qp = warp_sum(qp);
-                if (a.need_ortho) qo = warp_sum(qo);
-                if (my_c == c) { zlev = zl; qtot = my_para ? qp : qo; trot_mine = trot; }
+                if (a.need_para) qp = warp_sum_f32(qp);
+                if (a.need_ortho) qo = warp_sum_f32(qo);
+                if (my_c == c) { q32 = my_para ? qp : qo; trot_mine = trot; }
             }
-            // ---- P2: per (component, spectrum) scalars, lanes <-> pairs ----
+            // ---- P2: per (component, spectrum) scalars in FP64, lanes <-> pairs ----
             if (pair_lane) {
                 const NfSpecMeta &sm = a.spec[my_s];
                 const double voff = ld_param<PT>(a.params, pbase + 0 * NC + my_c);
@@ -235,6 +294,17 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                 const double sigm = ld_param<PT>(a.params, pbase + 4 * NC + my_c);
                 const double orth = ld_param<PT>(a.params, pbase + 5 * NC + my_c);
                 if (a.lte) tex = trot_mine;
+                const double a1 = NF_HK * (2.0 * NF_BROT + (NF_CROT - NF_BROT));
+                const double a2 = NF_HK * (6.0 * NF_BROT + 4.0 * (NF_CROT - NF_BROT));
+                const double lev1 = 3.0 * fastexp_f64(a1 / trot_mine);
+                const double lev2 = 5.0 * fastexp_f64(a2 / trot_mine);
+                double zlev = my_J == 1 ? lev1 : lev2;
+                if (my_J > 2) {
+                    const double J = (double)my_J;
+                    zlev = (2.0 * J + 1.0) *
+                           fastexp_f64(NF_HK * (NF_BROT * J * (J + 1.0) + (NF_CROT - NF_BROT) * J * J) / trot_mine);
+                }
+                const double qtot = my_para ? lev1 + lev2 + (double)q32 : (double)q32;
                 const double frac = my_para ? 1.0 - orth : orth;
                 const double pop = exp10(ntot) * frac * zlev / qtot;          // ammonia.pyx:353
                 const double e = exp(-sm.hnu_k / tex);                        // ammonia.pyx:354-357
@@ -274,64 +344,71 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
         double lnl = 0.0;
         for (int s = 0; s < a.n_spec; ++s) {
             const NfSpecMeta &sm = a.spec[s];
+            const double nu_min = sm.nu_min, inv_chan = sm.inv_chan;
+            const float t0a = sm.t0a, t0b = sm.t0b;
             // ---- P3: per-line window + Gaussian coefficients, lanes <-> lines ----
             uint32_t lohi[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int nl = IS_NH3 ? sm.nlines : ncomp;
                 const bool act = lane < nl;
-                double f, soc, voc, wT, nucen, w;
+                double nucen, w;
+                float wT;
                 if (IS_NH3) {
-                    f = act ? g_line_freq[sm.line_off + lane] : sm.nu0;
-                    soc = sc.soc[c]; voc = sc.voc[c];
-                    wT = act ? sc.tauT[c][s] * g_line_wt[sm.line_off + lane] : 0.0;
-                    w = soc * f;                  // hyperfine.pyx:71
-                    nucen = f - voc * f;          // hyperfine.pyx:72-73
+                    const double f = act ? g_line_freq[sm.line_off + lane] : sm.nu0;
+                    wT = act ? (float)sc.tauT[c][s] * (float)g_line_wt[sm.line_off + lane] : 0.0f;
+                    w = sc.soc[c] * f;                  // hyperfine.pyx:71
+                    nucen = f - sc.voc[c] * f;          // hyperfine.pyx:72-73
                 } else {
-                    f = sm.nu0;                   // gaussian.pyx:28-33
+                    const double f = sm.nu0;            // gaussian.pyx:28-33
                     const int cl = act ? lane : 0;
                     const double voff = ld_param<PT>(a.params, pbase + cl);
                     const double sigm = ld_param<PT>(a.params, pbase + ncomp + cl);
-                    wT = act ? ld_param<PT>(a.params, pbase + 2 * ncomp + cl) : 0.0;
+                    wT = act ? (float)ld_param<PT>(a.params, pbase + 2 * ncomp + cl) : 0.0f;
                     w = sigm / NF_CKMS * f;
                     nucen = f * (1.0 - voff / NF_CKMS);
                 }
                 const double cut = 5.0 * fabs(w);          // sqrt(12.5 / (0.5 / w^2)), hyperfine.pyx:82
-                const double rel = nucen - sm.nu_min;
-                const double nmax = (double)a.n_chan;
-                // floor((nu_cen - nu_min -/+ cut) / nu_chan), hyperfine.pyx:83-87
-                double flo = floor((rel - cut) / sm.nu_chan), fhi = floor((rel + cut) / sm.nu_chan);
-                flo = fmax(fmin(flo, nmax), -1.0);          // NaN -> out of range -> skipped
-                fhi = fmax(fmin(fhi, nmax), -1.0);
-                if (!(flo == flo) || !(fhi == fhi)) { flo = nmax; fhi = -1.0; }
-                int lo = (int)flo, hi = (int)fhi;
+                const double rel = nucen - nu_min;
+                // floor((nu_cen - nu_min -/+ cut) / nu_chan), hyperfine.pyx:83-87.  cvt.rmi saturates
+                // and maps NaN to 0, so non-finite parameters end up with an empty window.
+                int lo = __double2int_rd((rel - cut) * inv_chan);
+                int hi = __double2int_rd((rel + cut) * inv_chan);
                 bool on = act && !(hi < 0 || lo > a.n_chan - 1);   // hyperfine.pyx:88
                 lo = max(lo, 0);
                 hi = min(hi, a.n_chan - 1);
                 on = on && hi > lo;                                // loop j in [lo, hi)
-                const double jc = rel * sm.inv_chan;
-                double R = rint(jc);
-                R = fmax(fmin(R, 1.0e7), -1.0e7);
-                const double phi = jc - R;
-                const double sch = w * sm.inv_chan;
-                const double k2 = 0.5 / (sch * sch) * NF_LOG2E;
-                float4 A, Bv;
-                A.x = (float)R; A.y = (float)(-k2); A.z = (float)(2.0 * k2 * phi); A.w = (float)(-k2 * phi * phi);
-                Bv.x = on ? (float)wT : 0.0f;
-                Bv.y = on ? (float)((double)lo - R) : 0.0f;
-                Bv.z = on ? (float)((double)hi - R) : 0.0f;
-                Bv.w = 0.0f;
-                if (!on) { A.x = 0.f; A.y = 0.f; A.z = 0.f; A.w = 0.f; }
-                sc.lineA[c][lane] = A;
-                sc.lineB[c][lane] = Bv;
+                const double jc = rel * inv_chan;
+                const int Ri = __double2int_rn(jc);
+                const float phi = (float)(jc - (double)Ri);
+                const float sch = (float)(w * inv_chan);
+                const float k2 = __fdividef(0.5f * (float)NF_LOG2E, sch * sch);
+                float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 Bw = make_float2(0.f, 0.f);
+                if (on) {
+                    A.x = (float)Ri;
+                    A.y = -k2;
+                    A.z = 2.0f * k2 * phi;
+                    A.w = wT * ex2_approx(-k2 * phi * phi);
+                    Bw.x = (float)(lo - Ri);
+                    Bw.y = (float)(hi - Ri);
+                }
+                sc.line[c][lane].a = A;
+                sc.line[c][lane].w = Bw;
                 lohi[c] = on ? ((uint32_t)lo | ((uint32_t)hi << 16)) : 0u;
             }
             __syncwarp();
             if (!data_ready) { mbar_wait(bar, 0); data_ready = true; }
 
-            const bool staged = have_data && pix == pix0;
-            const float *grow = have_data ? a.data + pix * a.pix_stride + (int64_t)s * a.n_pad : nullptr;
-            const float *srow = sdata + s * a.n_pad;
+            float4 ampc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) ampc[c] = IS_NH3 ? sc.amp[c][s] : make_float4(0.f, 0.f, 0.f, 0.f);
+
+            // this pixel's row: the CTA's staged copy in shared memory when the vector belongs to
+            // the tile's pixel, else straight from HBM/L2 (generic pointer, one LD per chunk)
+            const float *drow = nullptr;
+            if (have_data)
+                drow = (pix == pix0 ? sdata + s * a.n_pad : a.data + pix * a.pix_stride + (int64_t)s * a.n_pad) + lane;
             float acc = 0.0f;
             for (int sb = 0; sb < nchunks; sb += 32) {
                 uint32_t cm[NC], un[NC];
@@ -348,43 +425,56 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                     cm[c] = m;
                     un[c] = __reduce_or_sync(NF_FULL, m);
                 }
+                uint32_t un_any = 0u;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) un_any |= un[c];
                 const int cend = min(32, nchunks - sb);
-                for (int cc = 0; cc < cend; ++cc) {
-                    const int j = ((sb + cc) << 5) + lane;
-                    const float xj = (float)((sb + cc) << 5) + xl;
+                float xj = (float)((sb << 5) + lane);
+                for (int cc = 0; cc < cend; ++cc, xj += 32.0f) {
+                    const int g = sb + cc;
                     float d = 0.0f;
-                    if (have_data) d = staged ? srow[j] : __ldg(grow + j);
+                    if (have_data) d = drow[g << 5];
+                    if (!((un_any >> cc) & 1u)) {          // no line of any component touches this chunk
+                        if (WRITE_PRED) {
+                            const int j = (g << 5) + lane;
+                            if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
+                        }
+                        acc = fmaf(d, d, acc);
+                        continue;
+                    }
+                    const float T0 = fmaf(t0b, xj, t0a);
                     float m = 0.0f;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         if (!((un[c] >> cc) & 1u)) continue;
                         uint32_t lm = __ballot_sync(NF_FULL, (cm[c] >> cc) & 1u);
                         float tau = 0.0f;
-                        while (lm) {
-                            const int i = __ffs(lm) - 1;
-                            lm &= lm - 1;
-                            const float4 A = sc.lineA[c][i];
-                            const float4 Bv = sc.lineB[c][i];
-                            const float d0 = xj - A.x;
-                            const float t = fmaf(A.y, d0, A.z);
-                            const float e = ex2_approx(fmaf(t, d0, A.w));
-                            if (d0 >= Bv.y && d0 < Bv.z) tau = fmaf(Bv.x, e, tau);
-                        }
                         if (IS_NH3) {
-                            const float4 am = sc.amp[c][s];
-                            const float T0 = fmaf(sm.t0b, xj, sm.t0a);
+                            // lines are sorted in frequency with equal widths: the set that touches
+                            // a chunk is a contiguous run [first, first + cnt)
+                            const int first = __ffs(lm) - 1, cnt = __popc(lm);
+                            const LineRec *rec = &sc.line[c][first];
+                            const LineRec *rend = rec + cnt;
+#pragma unroll 2
+                            for (; rec != rend; ++rec) line_term(tau, rec, xj);
+                            const float4 am = ampc[c];
                             const float D = fmaxf(fmaf(am.y, xj, am.x), fmaf(am.w, xj, am.z));
-                            float e1;
-                            if (fabsf(tau) < 0.03125f)   // FastExp Taylor branch, fastexp.c:265-270
-                                e1 = tau * (1.0f - 0.5f * tau * (1.0f - tau * (1.0f / 3.0f)));
-                            else
-                                e1 = 1.0f - ex2_approx(-(float)NF_LOG2E * tau);
+                            // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
+                            const float e1s = tau * (1.0f - 0.5f * tau * (1.0f - tau * (1.0f / 3.0f)));
+                            const float e1l = 1.0f - ex2_approx(-(float)NF_LOG2E * tau);
+                            const float e1 = fabsf(tau) < 0.03125f ? e1s : e1l;
                             m = fmaf(T0 * D, e1, m);
                         } else {
+                            while (lm) {
+                                const int i = __ffs(lm) - 1;
+                                lm &= lm - 1;
+                                line_term(tau, &sc.line[c][i], xj);
+                            }
                             m += tau;
                         }
                     }
                     if (WRITE_PRED) {
+                        const int j = (g << 5) + lane;
                         if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = m;
                     }
                     const float r = d - m;
