@@ -141,6 +141,51 @@ int nf_prior_transform(const nf_priors *pr, double *u_dev, int64_t B, int ncomp,
                        void *stream);
 int nf_prior_transform_host(const nf_priors *pr, double *u_host, int64_t B, int ncomp);
 
+/* ---- batched nested sampling (replaces the per-pixel MultiNest loop) ------ */
+/*
+ * MultiNest's `run(IS, mmodal, ceff, nlive, tol, efr, ndims, nPar, ..., LogLike,
+ * dumper, context)` (cmultinest.pxd:5-33) fits ONE pixel per call through a C
+ * callback.  nf_ns_* fits a block of "runs" (pixel, ncomp) in lock-step: every
+ * iteration draws `n_prop` proposals per in-flight run from the constrained
+ * prior, maps them through the device prior transform and scores all of them
+ * with one launch of the fused likelihood kernel.  The knobs keep MultiNest's
+ * names and meaning where they exist (run_multinest, core.pyx:727-732).
+ */
+typedef struct nf_ns_config {
+    int32_t nlive_max;   /* capacity of the live set; per-run nlive <= nlive_max       */
+    int32_t n_prop;      /* proposals per run per lock-step iteration (K)              */
+    int32_t max_iter;    /* `maxiter`: cap on nested-sampling iterations per run       */
+    int32_t max_samples; /* capacity of the posterior sample (dead + final live pts)   */
+    int32_t bound_update_interval; /* `walks`: random-walk steps per new point (<=1: 20+ndim) */
+    int32_t flags;       /* 0 auto: ellipsoidal rejection, random walk once it stalls;
+                            1 random walk from the start; 2 ellipsoidal rejection only   */
+    double tol;          /* `tol`: stop when ln(Z + Lmax X) - ln Z < tol               */
+    double efr;          /* `efr`: target sampling efficiency (ellipsoid enlargement)  */
+    uint64_t seed;       /* counter-based RNG seed: results are reproducible           */
+} nf_ns_config;
+
+/* pix_ids[n_run], nlive[n_run] are host arrays (nlive per run: main.py:445-447).
+ * `model_flags` = NF_FLAG_COLD | NF_FLAG_LTE for the NH3 model. */
+int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_flags,
+                 const nf_ns_config *cfg, int64_t n_run, const int32_t *pix_ids,
+                 const int32_t *nlive, nf_sampler **out);
+int nf_ns_run(nf_sampler *s);
+int nf_ns_free(nf_sampler *s);
+/* What the reference's dumper receives per run (core.pyx:627-687): ln Z
+ * (`global_lnZ`), its error sqrt(H/nlive), max log-likelihood, number of posterior
+ * samples, plus iteration / likelihood-evaluation counts; bestfit = maximum-
+ * likelihood sample, mapfit = sample of largest posterior weight.  All host arrays
+ * of n_run (x ndim) entries; any may be NULL. */
+int nf_ns_results(const nf_sampler *s, double *lnZ, double *lnZ_err, double *max_lnL,
+                  int32_t *n_samples, int32_t *n_iter, int64_t *n_evals,
+                  double *bestfit, double *mapfit);
+/* Posterior sample of one run: theta [n][ndim] FP32 (the reference stores the
+ * posterior as float32, core.pyx:680), lnL [n], ln prior-mass weight lnw [n];
+ * posterior weight p_i = exp(lnL_i + lnw_i - lnZ).  n = min(n_samples, capacity). */
+int nf_ns_posterior(const nf_sampler *s, int64_t run, int32_t capacity, float *theta,
+                    double *lnL, double *lnw);
+int nf_ns_stats(const nf_sampler *s, int32_t *lock_iters, int64_t *launches);
+
 /* ---- kernel timing helper (bench / roofline) ---------------------------- */
 /* Milliseconds the last *_host call spent in kernels only (CUDA events on the
  * launching streams), and how many kernels it launched. */

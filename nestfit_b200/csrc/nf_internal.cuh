@@ -84,6 +84,7 @@ struct NfLikeArgs {
     int ncomp, n_spec, n_chan, n_pad;
     int cold, lte;
     int need_para, need_ortho;
+    int tile_vecs;              // parameter vectors per CTA tile (0 -> NF_TILE_VECS)
     NfSpecMeta spec[NF_MAX_SPEC];
 };
 

@@ -234,7 +234,8 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpScratch<NC> &sc = scr_all[warp];
 
-    const int64_t b0 = (int64_t)blockIdx.x * NF_TILE_VECS;
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    const int64_t b0 = (int64_t)blockIdx.x * tile;
     constexpr bool have_data = !WRITE_PRED;
     int64_t pix0 = 0;
     if (have_data) {
@@ -251,7 +252,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     const int nchunks = (a.n_chan + 31) >> 5;
     const uint32_t sdata_addr = smem_u32(sdata) + (uint32_t)lane * 4u;
 
-    for (int64_t b = b0 + warp; b < b0 + NF_TILE_VECS && b < a.B; b += NF_WARPS_PER_CTA) {
+    for (int64_t b = b0 + warp; b < b0 + tile && b < a.B; b += NF_WARPS_PER_CTA) {
         const int64_t pbase = b * ndim;
         int64_t pix = 0;
         if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;
@@ -507,7 +508,8 @@ static cudaError_t launch_one(const NfLikeArgs &a, cudaStream_t st)
     size_t smem = like_smem_bytes<NC>(a);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
-    int64_t grid = (a.B + NF_TILE_VECS - 1) / NF_TILE_VECS;
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    int64_t grid = (a.B + tile - 1) / tile;
     if (grid <= 0) return cudaSuccess;
     kern<<<(unsigned)grid, NF_THREADS, smem, st>>>(a);
     return cudaGetLastError();

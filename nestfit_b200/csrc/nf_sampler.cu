@@ -1,0 +1,852 @@
+// Batched nested-sampling driver: many pixels ("runs") advance in lock-step and
+// every iteration's constrained-prior proposals of all in-flight pixels are
+// scored by ONE launch of the fused likelihood kernel.
+//
+// It replaces the reference's per-pixel, serial MultiNest callback loop
+//   run_multinest -> MultiNest `run` -> mn_loglikelihood -> Runner.c_loglikelihood
+//   (nestfit/core/core.pyx:622-624,727-823; nestfit/core/cmultinest.pxd:5-33)
+// and produces what `mn_dump` (core.pyx:627-687) persists: ln Z, its error,
+// max log-likelihood, the weighted posterior sample, best-fit and MAP vectors.
+// MultiNest itself (Feroz & Hobson 2008; Feroz, Hobson & Bridges 2009) is an
+// external, un-vendored Fortran library: this is an algorithmic replacement with
+// the same published scheme, not a port -- ln Z / posterior parity is
+// statistical ("parity unpinned").
+//
+// Algorithm per run (all in the unit cube, FP64):
+//   live set of `nlive` points; per lock-step iteration K candidates are drawn
+//   uniformly from a bounding ellipsoid of the live set (enlarged to the larger
+//   of 1.2 x the bounding volume and X_i / efr, MultiNest's `efr`; the unit cube
+//   itself while that volume is >= 1/2), transformed to physical parameters,
+//   scored, and then consumed *in order*: candidate k replaces the current worst
+//   live point iff lnL_k > lnL_worst, which records the worst point as a dead
+//   point with prior-mass weight X_{i-1} - X_i, X_i = exp(-i / nlive).  A
+//   candidate tested against the then-current threshold is an exact rejection
+//   sample of the constrained prior, so no proposal is wasted by the batching.
+//   Termination (MultiNest `tol`): ln(Z + L_max X_i) - ln Z < tol; the remaining
+//   live points are then added with weight X_i / nlive.
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "nf_internal.cuh"
+
+#define NS_MAX_DIM 32
+#define NS_FULL 0xffffffffu
+
+struct nf_sampler {
+    const nf_pixels *px;
+    const nf_priors *pr;
+    int device, ncomp, flags, ndim;
+    nf_ns_config cfg;
+    int64_t n_run;
+    int K;
+    // device state
+    int32_t *pix_ids, *nlive;          // [n_run]
+    double *live_u, *live_th, *live_l; // [n_run][nlive_max][ndim], .., [n_run][nlive_max]
+    double *cand_u, *cand_th, *cand_l; // [n_run][K][ndim], .., [n_run][K]
+    int32_t *cand_pix;                 // [n_run][K]
+    double *bound;                     // [n_run][ndim + ndim*ndim + 2]: mean, scaled L, {use_cube, -}
+    float *dead_th;                    // [n_run][max_samples][ndim]
+    double *dead_l, *dead_lw;          // [n_run][max_samples]
+    double *lnZ, *H, *lmax;            // [n_run]
+    int32_t *n_dead, *it, *done, *n_it_lock;
+    int64_t *n_eval;
+    double *bestfit, *mapfit, *lnZ_err; // [n_run][ndim] x2, [n_run]
+    int32_t *act;                      // [n_run] active run list
+    int32_t *n_act_dev;
+    // constrained random walk (used when ellipsoidal rejection sampling stalls)
+    int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
+    double *lstar, *scale, *chain_u, *chain_th, *chain_l;
+    int walks;
+    int32_t *n_act_host;               // pinned
+    cudaStream_t stream;
+    int lock_iters;
+    int64_t launches;
+};
+
+namespace {
+
+// ---- Philox4x32-10 counter-based RNG ---------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                             uint32_t k1)
+{
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+
+struct Philox {
+    uint32_t c[4], k[2], out[4];
+    int have;
+    __device__ Philox(uint64_t seed, uint32_t a, uint32_t b, uint32_t cidx)
+    {
+        k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
+        c[0] = 0; c[1] = a; c[2] = b; c[3] = cidx;
+        have = 0;
+    }
+    __device__ void refill()
+    {
+        uint32_t x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], k0 = k[0], k1 = k[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(x0, x1, x2, x3, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+        c[0]++;
+        have = 4;
+    }
+    __device__ uint32_t next()
+    {
+        if (!have) refill();
+        return out[--have];
+    }
+    // uniform in (0,1), 53 bits
+    __device__ double uniform()
+    {
+        const uint64_t a = next(), b = next();
+        const uint64_t v = ((a << 32) | b) >> 11;
+        return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    __device__ void normal2(double &z0, double &z1)
+    {
+        const double u1 = uniform(), u2 = uniform();
+        const double r = sqrt(-2.0 * log(u1));
+        double s, c2;
+        sincospi(2.0 * u2, &s, &c2);
+        z0 = r * c2; z1 = r * s;
+    }
+};
+
+__device__ __forceinline__ double logaddexp(double a, double b)
+{
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    const double m = fmax(a, b);
+    return m + log1p(exp(-fabs(a - b)));
+}
+
+// ---- initial live points: uniform in the unit cube -------------------------
+__global__ void ns_init_live_kernel(double *live_u, double *live_th, int64_t n_run, int nlive_max, int ndim,
+                                    uint64_t seed)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (run, point)
+    if (idx >= n_run * nlive_max) return;
+    const int64_t r = idx / nlive_max;
+    const int p = (int)(idx - r * nlive_max);
+    Philox rng(seed, (uint32_t)r, 0xFFFFFFFFu, (uint32_t)p);
+    double *u = live_u + idx * ndim, *th = live_th + idx * ndim;
+    for (int k = 0; k < ndim; ++k) { const double v = rng.uniform(); u[k] = v; th[k] = v; }
+}
+
+__global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32_t *n_dead, int32_t *it,
+                                     int32_t *done, int64_t *n_eval, int32_t *act, const int32_t *nlive,
+                                     const double *live_l, int64_t n_run, int nlive_max, int32_t *mode,
+                                     int32_t *coh_step, int32_t *coh_acc, int32_t *eff_acc, int32_t *eff_prop,
+                                     double *scale, int start_mode)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_run) return;
+    mode[r] = start_mode; coh_step[r] = 0; coh_acc[r] = 0; eff_acc[r] = 0; eff_prop[r] = 0; scale[r] = 0.3;
+    lnZ[r] = -INFINITY; H[r] = 0.0; n_dead[r] = 0; it[r] = 0; done[r] = 0; n_eval[r] = nlive[r];
+    act[r] = (int32_t)r;
+    double m = -INFINITY;
+    for (int p = 0; p < nlive[r]; ++p) {
+        const double l = live_l[r * nlive_max + p];
+        if (l > m) m = l;
+    }
+    lmax[r] = m;
+}
+
+// ---- bounding ellipsoid of the live set (one CTA per active run) -----------
+__global__ void __launch_bounds__(128)
+ns_bounds_kernel(const int32_t *act, const int32_t *nlive_arr, const int32_t *it_arr, const double *live_u,
+                 double *bound, int nlive_max, int ndim, double efr)
+{
+    __shared__ double s_mean[NS_MAX_DIM];
+    __shared__ double s_c[NS_MAX_DIM][NS_MAX_DIM + 1];
+    __shared__ double s_red[128];
+    const int r = act[blockIdx.x];
+    const int nl = nlive_arr[r];
+    const int tid = threadIdx.x, d = ndim;
+    const double *U = live_u + (int64_t)r * nlive_max * d;
+    if (tid < d) {
+        double s = 0.0;
+        for (int p = 0; p < nl; ++p) s += U[p * d + tid];
+        s_mean[tid] = s / (double)nl;
+    }
+    __syncthreads();
+    const int npair = d * (d + 1) / 2;
+    for (int e = tid; e < npair; e += blockDim.x) {
+        // unpack (a >= b) from the triangular index
+        int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        while (a * (a + 1) / 2 > e) --a;
+        const int b = e - a * (a + 1) / 2;
+        double s = 0.0;
+        const double ma = s_mean[a], mb = s_mean[b];
+        for (int p = 0; p < nl; ++p) s += (U[p * d + a] - ma) * (U[p * d + b] - mb);
+        s /= (double)(nl > 1 ? nl - 1 : 1);
+        if (a == b) s += 1e-12;
+        s_c[a][b] = s;
+        s_c[b][a] = s;
+    }
+    __syncthreads();
+    // Cholesky (lower) in place by warp 0: lane <-> row
+    if (tid < 32) {
+        for (int j = 0; j < d; ++j) {
+            double djj = s_c[j][j];
+            for (int k = 0; k < j; ++k) djj -= s_c[j][k] * s_c[j][k];
+            djj = sqrt(fmax(djj, 1e-300));
+            __syncwarp();
+            if (tid == 0) s_c[j][j] = djj;
+            if (tid > j && tid < d) {
+                double v = s_c[tid][j];
+                for (int k = 0; k < j; ++k) v -= s_c[tid][k] * s_c[j][k];
+                s_c[tid][j] = v / djj;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // largest Mahalanobis radius over the live points
+    double fmx = 0.0;
+    for (int p = tid; p < nl; p += blockDim.x) {
+        double y[NS_MAX_DIM];
+        double r2 = 0.0;
+        for (int a = 0; a < d; ++a) {
+            double v = U[p * d + a] - s_mean[a];
+            for (int k = 0; k < a; ++k) v -= s_c[a][k] * y[k];
+            v /= s_c[a][a];
+            y[a] = v;
+            r2 += v * v;
+        }
+        fmx = fmax(fmx, r2);
+    }
+    s_red[tid] = fmx;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o) s_red[tid] = fmax(s_red[tid], s_red[tid + o]);
+        __syncthreads();
+    }
+    const double f = s_red[0];
+    // volumes: ln V = ln V_d + (d/2) ln f + sum ln L_jj
+    double lndet = 0.0;
+    for (int j = 0; j < d; ++j) lndet += log(s_c[j][j]);
+    const double lnVd = 0.5 * d * log(M_PI) - lgamma(0.5 * d + 1.0);
+    const double lnV_bound = lnVd + 0.5 * d * log(f) + lndet + log(1.2);
+    const double lnX = -(double)it_arr[r] / (double)nl;
+    const double lnV_target = lnX - log(efr);
+    const double lnV = fmax(lnV_bound, lnV_target);
+    // linear scale applied to L so that the ellipsoid has volume V
+    const double scale = exp((lnV - lnVd - lndet) / (double)d);
+    double *B = bound + (int64_t)r * (d + d * d + 2);
+    if (tid < d) B[tid] = s_mean[tid];
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        const int a = e / d, b = e - a * d;
+        B[d + e] = b <= a ? scale * s_c[a][b] : 0.0;
+    }
+    if (tid == 0) {
+        const bool degenerate = !(f > 0.0) || !isfinite(scale);
+        B[d + d * d] = (lnV > log(0.5) || degenerate) ? 1.0 : 0.0;   // sample the unit cube itself
+        B[d + d * d + 1] = lnV;
+    }
+}
+
+// Device-side view of the sampler state handed to the kernels by value.
+struct NsDev {
+    const int32_t *act;
+    int n_act;
+    const int32_t *pix_ids, *nlive;
+    double *live_u, *live_th, *live_l;
+    double *cand_u, *cand_th, *cand_l;
+    int32_t *cand_pix;
+    double *bound;
+    float *dead_th;
+    double *dead_l, *dead_lw;
+    double *lnZ, *H, *lmax;
+    int32_t *n_dead, *it, *done;
+    int64_t *n_eval;
+    // constrained random-walk state
+    int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
+    double *lstar, *scale, *chain_u, *chain_th, *chain_l;
+    int K, d, nlive_max, max_samples, max_iter, walks, flags;
+    double tol, efr;
+    uint64_t seed;
+    int lock;
+};
+
+// uniform point in the unit d-ball
+__device__ void unit_ball(Philox &rng, int d, double *y)
+{
+    double n2 = 0.0;
+    for (int j = 0; j < d; j += 2) {
+        double z0, z1;
+        rng.normal2(z0, z1);
+        y[j] = z0; n2 += z0 * z0;
+        if (j + 1 < d) { y[j + 1] = z1; n2 += z1 * z1; }
+    }
+    const double rad = pow(rng.uniform(), 1.0 / (double)d) / sqrt(n2);
+    for (int j = 0; j < d; ++j) y[j] *= rad;
+}
+
+// ---- proposals: K candidates (or K random-walk steps) per active run ---------
+__global__ void ns_propose_kernel(const NsDev D)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
+    if (idx >= D.n_act * D.K) return;
+    const int a = idx / D.K, k = idx - a * D.K;
+    const int r = D.act[a];
+    const int d = D.d;
+    const double *B = D.bound + (int64_t)r * (d + d * d + 2);
+    Philox rng(D.seed, (uint32_t)r, (uint32_t)D.lock, (uint32_t)k);
+    double u[NS_MAX_DIM], y[NS_MAX_DIM];
+    bool ok = false;
+    if (D.mode[r] == 0) {
+        // rejection sampling from the bounding ellipsoid (or the unit cube itself)
+        if (B[d + d * d] > 0.5) {
+            for (int j = 0; j < d; ++j) u[j] = rng.uniform();
+            ok = true;
+        } else {
+            for (int tries = 0; tries < 64 && !ok; ++tries) {
+                unit_ball(rng, d, y);
+                ok = true;
+                for (int i = 0; i < d; ++i) {
+                    double v = B[i];
+                    for (int j = 0; j <= i; ++j) v += B[d + i * d + j] * y[j];
+                    u[i] = v;
+                    if (!(v > 0.0 && v < 1.0)) ok = false;
+                }
+            }
+        }
+    } else {
+        // constrained random walk: chain k takes one step of size `scale` in the metric of the
+        // live set's bounding ellipsoid; a cohort of K chains starts from random live points
+        double *cu = D.chain_u + ((int64_t)r * D.K + k) * d;
+        if (D.coh_step[r] == 0) {
+            const int nl = D.nlive[r];
+            int j = (int)(rng.uniform() * (double)nl);
+            j = min(j, nl - 1);
+            const double *lu = D.live_u + ((int64_t)r * D.nlive_max + j) * d;
+            const double *lt = D.live_th + ((int64_t)r * D.nlive_max + j) * d;
+            double *ct = D.chain_th + ((int64_t)r * D.K + k) * d;
+            for (int i = 0; i < d; ++i) { cu[i] = lu[i]; ct[i] = lt[i]; }
+            D.chain_l[(int64_t)r * D.K + k] = D.live_l[(int64_t)r * D.nlive_max + j];
+            D.chain_moved[(int64_t)r * D.K + k] = 0;
+        }
+        unit_ball(rng, d, y);
+        const double sc = D.scale[r];
+        ok = true;
+        for (int i = 0; i < d; ++i) {
+            double v = 0.0;
+            for (int j = 0; j <= i; ++j) v += B[d + i * d + j] * y[j];
+            v = cu[i] + sc * v;
+            u[i] = v;
+            if (!(v > 0.0 && v < 1.0)) ok = false;
+        }
+    }
+    double *ou = D.cand_u + (int64_t)idx * d, *ot = D.cand_th + (int64_t)idx * d;
+    for (int j = 0; j < d; ++j) {
+        const double v = ok ? u[j] : nan("");    // NaN -> NaN lnL -> never accepted
+        ou[j] = v;
+        ot[j] = v;
+    }
+    D.cand_pix[idx] = D.pix_ids[r];
+}
+
+// Running state of one run held in registers by every lane of its warp.
+struct RunState {
+    double lnZ, H, lmax;
+    int it, nd;
+    bool done;
+};
+
+__device__ __forceinline__ void warp_argmin(const double *LL, int nl, int lane, double &mn, int &im)
+{
+    mn = INFINITY;
+    im = 0;
+    for (int p = lane; p < nl; p += 32) {
+        const double v = LL[p];
+        if (v < mn) { mn = v; im = p; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(NS_FULL, mn, o);
+        const int i2 = __shfl_xor_sync(NS_FULL, im, o);
+        if (v2 < mn || (v2 == mn && i2 < im)) { mn = v2; im = i2; }
+    }
+}
+
+// Nested-sampling step with candidate (cu, ct, lc): if it beats the current worst live
+// point, that point dies with prior-mass weight X_{i-1} - X_i and the candidate takes
+// its slot.  Warp-cooperative; returns true when the candidate was inserted.
+__device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshell, const double *cu,
+                           const double *ct, double lc, RunState &S)
+{
+    const int d = D.d;
+    double *LL = D.live_l + (int64_t)r * D.nlive_max;
+    double mn;
+    int im;
+    warp_argmin(LL, nl, lane, mn, im);
+    if (!(lc > mn)) return false;          // rejected (also NaN)
+    const double lnw = -(double)S.it / (double)nl + lnshell;
+    const double lw = mn + lnw;
+    const double lnZ_new = logaddexp(S.lnZ, lw);
+    if (lnZ_new > -INFINITY) {
+        const double t1 = exp(lw - lnZ_new) * mn;
+        const double t2 = (S.lnZ > -INFINITY) ? exp(S.lnZ - lnZ_new) * (S.H + S.lnZ) : 0.0;
+        S.H = t1 + t2 - lnZ_new;
+    }
+    S.lnZ = lnZ_new;
+    if (S.nd < D.max_samples) {
+        const double *th = D.live_th + ((int64_t)r * D.nlive_max + im) * d;
+        float *dt = D.dead_th + ((int64_t)r * D.max_samples + S.nd) * d;
+        for (int j = lane; j < d; j += 32) dt[j] = (float)th[j];
+        if (lane == 0) {
+            D.dead_l[(int64_t)r * D.max_samples + S.nd] = mn;
+            D.dead_lw[(int64_t)r * D.max_samples + S.nd] = lnw;
+        }
+        ++S.nd;
+    }
+    double *lu = D.live_u + ((int64_t)r * D.nlive_max + im) * d, *lt = D.live_th + ((int64_t)r * D.nlive_max + im) * d;
+    for (int j = lane; j < d; j += 32) { lu[j] = cu[j]; lt[j] = ct[j]; }
+    if (lane == 0) LL[im] = lc;
+    __syncwarp();
+    ++S.it;
+    S.lmax = fmax(S.lmax, lc);
+    // MultiNest `tol`: largest possible remaining contribution L_max X_i
+    const double lnX = -(double)S.it / (double)nl;
+    if (logaddexp(S.lnZ, S.lmax + lnX) - S.lnZ < D.tol) S.done = true;
+    if (S.it >= D.max_iter || S.nd + nl >= D.max_samples) S.done = true;
+    return true;
+}
+
+// ---- consume the scored proposals (one warp per active run) ------------------
+__global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= D.n_act) return;
+    const int r = D.act[w];
+    const int nl = D.nlive[r], d = D.d, K = D.K;
+    RunState S;
+    S.lnZ = D.lnZ[r]; S.H = D.H[r]; S.lmax = D.lmax[r]; S.it = D.it[r]; S.nd = D.n_dead[r]; S.done = false;
+    int64_t nev = D.n_eval[r];
+    // ln(1 - exp(-1/nlive)): ln of the prior-mass shell X_{i-1} - X_i relative to X_{i-1}
+    const double lnshell = log(-expm1(-1.0 / (double)nl));
+    const int64_t c0 = (int64_t)w * K;          // candidate slots of this run in this iteration
+    int mode = D.mode[r];
+    if (mode == 0) {
+        int n_ok = 0, n_acc = 0;
+        for (int k = 0; k < K && !S.done; ++k) {
+            const double *cu = D.cand_u + (c0 + k) * d;
+            if (cu[0] == cu[0]) { ++nev; ++n_ok; }
+            if (try_insert(D, r, nl, lane, lnshell, cu, D.cand_th + (c0 + k) * d, D.cand_l[c0 + k], S)) ++n_acc;
+        }
+        // windowed acceptance rate; fall back to the random walk when rejection sampling stalls
+        int ea = D.eff_acc[r] + n_acc, ep = D.eff_prop[r] + n_ok;
+        if (ep >= 512) {
+            if (!(D.flags & 2) && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
+                mode = 1;
+                if (lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
+            }
+            ea = 0; ep = 0;
+        }
+        if (lane == 0) { D.eff_acc[r] = ea; D.eff_prop[r] = ep; }
+    } else {
+        int step = D.coh_step[r];
+        double lstar;
+        if (step == 0) {                        // a new cohort: threshold = current worst live point
+            int im;
+            warp_argmin(D.live_l + (int64_t)r * D.nlive_max, nl, lane, lstar, im);
+            if (lane == 0) { D.lstar[r] = lstar; D.coh_acc[r] = 0; }
+        } else {
+            lstar = D.lstar[r];
+        }
+        int acc = 0, nok = 0;
+        for (int k = lane; k < K; k += 32) {
+            const double *cu = D.cand_u + (c0 + k) * d;
+            const double lc = D.cand_l[c0 + k];
+            const bool ok = cu[0] == cu[0];
+            if (ok) ++nok;
+            if (ok && lc > lstar) {
+                double *hu = D.chain_u + ((int64_t)r * K + k) * d, *ht = D.chain_th + ((int64_t)r * K + k) * d;
+                const double *ct = D.cand_th + (c0 + k) * d;
+                for (int j = 0; j < d; ++j) { hu[j] = cu[j]; ht[j] = ct[j]; }
+                D.chain_l[(int64_t)r * K + k] = lc;
+                D.chain_moved[(int64_t)r * K + k] = 1;
+                ++acc;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(NS_FULL, acc, o);
+            nok += __shfl_xor_sync(NS_FULL, nok, o);
+        }
+        nev += nok;
+        const int cacc = (step == 0 ? 0 : D.coh_acc[r]) + acc;
+        ++step;
+        __syncwarp();
+        if (step >= D.walks) {
+            // the cohort's end points are candidates for the then-current threshold, in order
+            for (int k = 0; k < K && !S.done; ++k) {
+                if (!D.chain_moved[(int64_t)r * K + k]) continue;      // never moved: still a live point
+                try_insert(D, r, nl, lane, lnshell, D.chain_u + ((int64_t)r * K + k) * d,
+                           D.chain_th + ((int64_t)r * K + k) * d, D.chain_l[(int64_t)r * K + k], S);
+            }
+            // step size follows the acceptance fraction (target 1/2)
+            const double facc = (double)cacc / (double)(K * D.walks);
+            double sc = D.scale[r] * exp((facc - 0.5) / (0.5 * (double)d));
+            sc = fmin(fmax(sc, 1e-5), 2.0);
+            if (lane == 0) D.scale[r] = sc;
+            step = 0;
+        }
+        if (lane == 0) { D.coh_step[r] = step; D.coh_acc[r] = cacc; }
+    }
+    if (lane == 0) {
+        D.lnZ[r] = S.lnZ; D.H[r] = S.H; D.lmax[r] = S.lmax; D.it[r] = S.it; D.n_dead[r] = S.nd; D.n_eval[r] = nev;
+        if (S.done) D.done[r] = 1;
+    }
+}
+
+// ---- active-list compaction (single CTA) -------------------------------------
+__global__ void __launch_bounds__(1024)
+ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t *n_act_host, int64_t n_run)
+{
+    __shared__ int s_cnt[1024];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_run; base += 1024) {
+        const int64_t r = base + tid;
+        const int keep = (r < n_run && !done[r]) ? 1 : 0;
+        s_cnt[tid] = keep;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {      // inclusive scan
+            const int v = tid >= o ? s_cnt[tid - o] : 0;
+            __syncthreads();
+            s_cnt[tid] += v;
+            __syncthreads();
+        }
+        if (keep) act[s_base + s_cnt[tid] - 1] = (int32_t)r;
+        __syncthreads();
+        if (tid == 1023) s_base += s_cnt[1023];
+        __syncthreads();
+    }
+    if (tid == 0) { *n_act_dev = s_base; *n_act_host = s_base; }
+}
+
+// ---- finalisation: add the live points, normalise, pick best-fit / MAP ------
+__global__ void __launch_bounds__(128)
+ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double *live_l, float *dead_th,
+                   double *dead_l, double *dead_lw, double *lnZ_a, double *H_a, int32_t *n_dead_a, const int32_t *it_a,
+                   double *lnZ_err, double *bestfit, double *mapfit, int64_t n_run, int ndim, int nlive_max,
+                   int max_samples)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_run) return;
+    const int nl = nlive_arr[r], d = ndim;
+    int nd = n_dead_a[r];
+    double lnZ = lnZ_a[r], H = H_a[r];
+    const double lnw_live = -(double)it_a[r] / (double)nl - log((double)nl);   // X_i / nlive
+    for (int p = 0; p < nl && nd < max_samples; ++p) {
+        const double l = live_l[r * nlive_max + p];
+        const double lw = l + lnw_live;
+        const double lnZ_new = logaddexp(lnZ, lw);
+        if (lnZ_new > -INFINITY) {
+            const double t1 = exp(lw - lnZ_new) * l;
+            const double t2 = (lnZ > -INFINITY) ? exp(lnZ - lnZ_new) * (H + lnZ) : 0.0;
+            H = t1 + t2 - lnZ_new;
+        }
+        lnZ = lnZ_new;
+        const double *th = live_th + (r * nlive_max + p) * d;
+        float *dt = dead_th + (r * max_samples + nd) * d;
+        for (int j = lane; j < d; j += 32) dt[j] = (float)th[j];
+        if (lane == 0) { dead_l[r * max_samples + nd] = l; dead_lw[r * max_samples + nd] = lnw_live; }
+        ++nd;
+    }
+    __syncwarp();
+    // best fit = max likelihood sample; MAP = sample of largest posterior weight L_i w_i
+    double bl = -INFINITY, bw = -INFINITY;
+    int bi = 0, wi = 0;
+    for (int p = lane; p < nd; p += 32) {
+        const double l = dead_l[r * max_samples + p], lw = l + dead_lw[r * max_samples + p];
+        if (l > bl) { bl = l; bi = p; }
+        if (lw > bw) { bw = lw; wi = p; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double l2 = __shfl_xor_sync(NS_FULL, bl, o);
+        const int i2 = __shfl_xor_sync(NS_FULL, bi, o);
+        if (l2 > bl || (l2 == bl && i2 < bi)) { bl = l2; bi = i2; }
+        const double w2 = __shfl_xor_sync(NS_FULL, bw, o);
+        const int j2 = __shfl_xor_sync(NS_FULL, wi, o);
+        if (w2 > bw || (w2 == bw && j2 < wi)) { bw = w2; wi = j2; }
+    }
+    for (int j = lane; j < d; j += 32) {
+        bestfit[r * d + j] = (double)dead_th[(r * max_samples + bi) * d + j];
+        mapfit[r * d + j] = (double)dead_th[(r * max_samples + wi) * d + j];
+    }
+    if (lane == 0) {
+        lnZ_a[r] = lnZ;
+        H_a[r] = H;
+        n_dead_a[r] = nd;
+        lnZ_err[r] = sqrt(fmax(H, 0.0) / (double)nl);
+    }
+}
+
+#define NS_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_t B, double *lnl)
+{
+    NS_CUDA(nf_launch_prior_transform(s->pr, params, B, s->ncomp, s->stream));
+    NfLikeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    const nf_pixels *px = s->px;
+    a.data = px->data; a.inv2s2 = px->inv2s2; a.params = params; a.pix_of_vec = pix; a.vecs_per_pix = 1;
+    a.B = B; a.pix_stride = (int64_t)px->n_spec * px->n_pad; a.lnL = lnl; a.pred = nullptr; a.param_f64 = 1;
+    a.ncomp = s->ncomp; a.n_spec = px->n_spec; a.n_chan = px->n_chan; a.n_pad = px->n_pad;
+    a.cold = (s->flags & NF_FLAG_COLD) != 0; a.lte = (s->flags & NF_FLAG_LTE) != 0;
+    a.tile_vecs = (int)(vpp > 0 ? vpp : 0);     // one CTA tile = the proposals of one run (one pixel)
+    for (int k = 0; k < px->n_spec; ++k) {
+        a.spec[k] = px->spec[k];
+        if (px->spec[k].para) a.need_para = 1; else a.need_ortho = 1;
+    }
+    NS_CUDA(px->model == NF_MODEL_NH3 ? nf_launch_nh3(a, s->stream) : nf_launch_gauss(a, s->stream));
+    s->launches += 2;
+    return NF_OK;
+}
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+
+}  // namespace
+
+extern "C" {
+
+int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_flags, const nf_ns_config *cfg,
+                 int64_t n_run, const int32_t *pix_ids, const int32_t *nlive, nf_sampler **out)
+{
+    if (!out) return NF_EINVAL;
+    *out = nullptr;
+    if (!px || !pr || !cfg || !pix_ids || !nlive || n_run < 1 || ncomp < 1) return NF_EINVAL;
+    if (px->device != pr->device) return NF_EINVAL;
+    const int n_model = px->model == NF_MODEL_NH3 ? 6 : 3;
+    if (pr->n_model != n_model) return NF_EINVAL;
+    const int ndim = n_model * ncomp;
+    if (ndim > NS_MAX_DIM) return NF_EINVAL;
+    if (px->model == NF_MODEL_NH3 && ncomp > NF_MAX_NCOMP_NH3) return NF_EINVAL;
+    if (cfg->nlive_max < 8 || cfg->n_prop < 1 || cfg->max_samples < 2 * cfg->nlive_max || !(cfg->tol > 0.0) ||
+        !(cfg->efr > 0.0 && cfg->efr <= 1.0) || cfg->max_iter < 1)
+        return NF_EINVAL;
+    for (int64_t r = 0; r < n_run; ++r) {
+        if (pix_ids[r] < 0 || pix_ids[r] >= px->n_pix) return NF_EINVAL;
+        if (nlive[r] < 8 || nlive[r] > cfg->nlive_max) return NF_EINVAL;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(px->device) != cudaSuccess) return NF_ENODEV;
+    nf_sampler *s = new (std::nothrow) nf_sampler();
+    if (!s) return NF_ENOMEM;
+    std::memset(s, 0, sizeof(*s));
+    s->px = px; s->pr = pr; s->device = px->device; s->ncomp = ncomp; s->flags = model_flags; s->ndim = ndim;
+    s->cfg = *cfg; s->n_run = n_run; s->K = cfg->n_prop;
+    const size_t R = (size_t)n_run, NL = (size_t)cfg->nlive_max, D = (size_t)ndim, K = (size_t)s->K,
+                 MS = (size_t)cfg->max_samples;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    A(dalloc(&s->pix_ids, R)); A(dalloc(&s->nlive, R));
+    A(dalloc(&s->live_u, R * NL * D)); A(dalloc(&s->live_th, R * NL * D)); A(dalloc(&s->live_l, R * NL));
+    A(dalloc(&s->cand_u, R * K * D)); A(dalloc(&s->cand_th, R * K * D)); A(dalloc(&s->cand_l, R * K));
+    A(dalloc(&s->cand_pix, R * K));
+    A(dalloc(&s->bound, R * (D + D * D + 2)));
+    A(dalloc(&s->dead_th, R * MS * D)); A(dalloc(&s->dead_l, R * MS)); A(dalloc(&s->dead_lw, R * MS));
+    A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
+    A(dalloc(&s->n_dead, R)); A(dalloc(&s->it, R)); A(dalloc(&s->done, R)); A(dalloc(&s->n_eval, R));
+    A(dalloc(&s->bestfit, R * D)); A(dalloc(&s->mapfit, R * D));
+    A(dalloc(&s->act, R)); A(dalloc(&s->n_act_dev, 1));
+    A(dalloc(&s->mode, R)); A(dalloc(&s->coh_step, R)); A(dalloc(&s->coh_acc, R)); A(dalloc(&s->eff_acc, R));
+    A(dalloc(&s->eff_prop, R)); A(dalloc(&s->chain_moved, R * K)); A(dalloc(&s->lstar, R)); A(dalloc(&s->scale, R));
+    A(dalloc(&s->chain_u, R * K * D)); A(dalloc(&s->chain_th, R * K * D)); A(dalloc(&s->chain_l, R * K));
+    s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + ndim;
+    A(cudaMallocHost((void **)&s->n_act_host, sizeof(int32_t)));
+    A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->nlive, nlive, R * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) { nf_ns_free(s); return (int)e; }
+    *out = s;
+    return NF_OK;
+}
+
+int nf_ns_free(nf_sampler *s)
+{
+    if (!s) return NF_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->pix_ids, s->nlive, s->live_u, s->live_th, s->live_l, s->cand_u, s->cand_th, s->cand_l,
+                    s->cand_pix, s->bound, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->lmax, s->lnZ_err,
+                    s->n_dead, s->it, s->done, s->n_eval, s->bestfit, s->mapfit, s->act, s->n_act_dev,
+                    s->mode, s->coh_step, s->coh_acc, s->eff_acc, s->eff_prop, s->chain_moved, s->lstar, s->scale,
+                    s->chain_u, s->chain_th, s->chain_l};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (s->n_act_host) cudaFreeHost(s->n_act_host);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete s;
+    return NF_OK;
+}
+
+int nf_ns_run(nf_sampler *s)
+{
+    if (!s) return NF_EINVAL;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(s->device) != cudaSuccess) return NF_ENODEV;
+    const int d = s->ndim, NL = s->cfg.nlive_max, K = s->K;
+    const int64_t R = s->n_run;
+    cudaStream_t st = s->stream;
+    int rc = NF_OK;
+    // initial live points: uniform cube draws, scored in one batch
+    {
+        const int64_t n = R * NL;
+        ns_init_live_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->live_u, s->live_th, R, NL, d, s->cfg.seed);
+        // pixel of every (run, point): reuse cand_pix-like map built on the fly via vecs_per_pix is not
+        // possible (runs index arbitrary pixels), so score run by run blocks through an explicit map
+        int32_t *map = nullptr;
+        if (cudaMalloc((void **)&map, (size_t)n * sizeof(int32_t)) != cudaSuccess) { rc = NF_ENOMEM; }
+        if (rc == NF_OK) {
+            std::vector<int32_t> h((size_t)n), ids((size_t)R);
+            cudaMemcpy(ids.data(), s->pix_ids, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            for (int64_t r = 0; r < R; ++r)
+                for (int p = 0; p < NL; ++p) h[(size_t)(r * NL + p)] = ids[(size_t)r];
+            cudaMemcpyAsync(map, h.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            rc = score(s, s->live_th, map, NL, n, s->live_l);
+            cudaStreamSynchronize(st);
+            cudaFree(map);
+        }
+        if (rc == NF_OK) {
+            ns_init_state_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(s->lnZ, s->H, s->lmax, s->n_dead, s->it,
+                                                                            s->done, s->n_eval, s->act, s->nlive,
+                                                                            s->live_l, R, NL, s->mode, s->coh_step,
+                                                                            s->coh_acc, s->eff_acc, s->eff_prop,
+                                                                            s->scale, (s->cfg.flags & 1) ? 1 : 0);
+            s->launches += 2;
+        }
+    }
+    int n_act = (int)R;
+    int lock = 0;
+    // lock-step iterations are bounded: a run needs at most max_iter * walks of them
+    const int64_t lock_cap = (int64_t)s->cfg.max_iter * (int64_t)(s->walks + 1);
+    while (rc == NF_OK && n_act > 0 && (int64_t)lock < lock_cap && lock < 2000000000) {
+        NsDev D;
+        D.act = s->act; D.n_act = n_act; D.pix_ids = s->pix_ids; D.nlive = s->nlive;
+        D.live_u = s->live_u; D.live_th = s->live_th; D.live_l = s->live_l;
+        D.cand_u = s->cand_u; D.cand_th = s->cand_th; D.cand_l = s->cand_l; D.cand_pix = s->cand_pix;
+        D.bound = s->bound; D.dead_th = s->dead_th; D.dead_l = s->dead_l; D.dead_lw = s->dead_lw;
+        D.lnZ = s->lnZ; D.H = s->H; D.lmax = s->lmax; D.n_dead = s->n_dead; D.it = s->it; D.done = s->done;
+        D.n_eval = s->n_eval; D.mode = s->mode; D.coh_step = s->coh_step; D.coh_acc = s->coh_acc;
+        D.eff_acc = s->eff_acc; D.eff_prop = s->eff_prop; D.chain_moved = s->chain_moved; D.lstar = s->lstar;
+        D.scale = s->scale; D.chain_u = s->chain_u; D.chain_th = s->chain_th; D.chain_l = s->chain_l;
+        D.K = K; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
+        D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
+        D.lock = lock;
+        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->nlive, s->it, s->live_u, s->bound, NL, d, s->cfg.efr);
+        const int nc = n_act * K;
+        ns_propose_kernel<<<(nc + 127) / 128, 128, 0, st>>>(D);
+        rc = score(s, s->cand_th, s->cand_pix, K, nc, s->cand_l);
+        if (rc != NF_OK) break;
+        ns_update_kernel<<<(n_act * 32 + 127) / 128, 128, 0, st>>>(D);
+        ns_compact_kernel<<<1, 1024, 0, st>>>(s->done, s->act, s->n_act_dev, s->n_act_host, R);
+        s->launches += 4;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        n_act = *s->n_act_host;
+        ++lock;
+        if (getenv("NF_NS_DEBUG") && (lock % atoi(getenv("NF_NS_DEBUG"))) == 0 && n_act > 0) {
+            // diagnostics of the first still-active run
+            int32_t r0 = 0, it0 = 0; int64_t ne = 0; double z0 = 0, lm = 0;
+            cudaMemcpy(&r0, s->act, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&it0, s->it + r0, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&ne, s->n_eval + r0, 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&z0, s->lnZ + r0, 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&lm, s->lmax + r0, 8, cudaMemcpyDeviceToHost);
+            std::vector<double> B((size_t)(d + d * d + 2));
+            cudaMemcpy(B.data(), s->bound + (size_t)r0 * (d + d * d + 2), B.size() * 8, cudaMemcpyDeviceToHost);
+            std::vector<double> cu((size_t)K * d);
+            cudaMemcpy(cu.data(), s->cand_u, cu.size() * 8, cudaMemcpyDeviceToHost);   // slot 0 = first active run
+            int valid = 0;
+            for (int k = 0; k < K; ++k) if (cu[(size_t)k * d] == cu[(size_t)k * d]) ++valid;
+            int32_t md = 0; double sc = 0;
+            cudaMemcpy(&md, s->mode + r0, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&sc, s->scale + r0, 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[ns] lock %d n_act %d run %d mode %d scale %.3g it %d evals %lld lnZ %.3f lmax %.3f cube %.0f lnV %.2f valid %d/%d diagL:",
+                    lock, n_act, r0, md, sc, it0, (long long)ne, z0, lm, B[d + d * d], B[d + d * d + 1], valid, K);
+            for (int j = 0; j < d; ++j) fprintf(stderr, " %.3g", B[d + j * d + j]);
+            fprintf(stderr, "\n");
+        }
+    }
+    if (rc == NF_OK) {
+        ns_finalize_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(
+            s->nlive, s->live_th, s->live_l, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->n_dead, s->it,
+            s->lnZ_err, s->bestfit, s->mapfit, R, d, NL, s->cfg.max_samples);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = (int)e;
+        s->launches += 1;
+    }
+    s->lock_iters = lock;
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+int nf_ns_results(const nf_sampler *s, double *lnZ, double *lnZ_err, double *max_lnL, int32_t *n_samples,
+                  int32_t *n_iter, int64_t *n_evals, double *bestfit, double *mapfit)
+{
+    if (!s) return NF_EINVAL;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(s->device) != cudaSuccess) return NF_ENODEV;
+    const size_t R = (size_t)s->n_run, D = (size_t)s->ndim;
+    cudaError_t e = cudaSuccess;
+    auto C = [&](void *dst, const void *src, size_t n) { if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost); };
+    C(lnZ, s->lnZ, R * 8); C(lnZ_err, s->lnZ_err, R * 8); C(max_lnL, s->lmax, R * 8);
+    C(n_samples, s->n_dead, R * 4); C(n_iter, s->it, R * 4); C(n_evals, s->n_eval, R * 8);
+    C(bestfit, s->bestfit, R * D * 8); C(mapfit, s->mapfit, R * D * 8);
+    if (prev >= 0) cudaSetDevice(prev);
+    return (int)e;
+}
+
+int nf_ns_posterior(const nf_sampler *s, int64_t run, int32_t capacity, float *theta, double *lnL, double *lnw)
+{
+    if (!s || run < 0 || run >= s->n_run || capacity < 0) return NF_EINVAL;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(s->device) != cudaSuccess) return NF_ENODEV;
+    int32_t n = 0;
+    cudaError_t e = cudaMemcpy(&n, s->n_dead + run, 4, cudaMemcpyDeviceToHost);
+    if (n > capacity) n = capacity;
+    const size_t MS = (size_t)s->cfg.max_samples, D = (size_t)s->ndim;
+    if (e == cudaSuccess && theta) e = cudaMemcpy(theta, s->dead_th + (size_t)run * MS * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lnL) e = cudaMemcpy(lnL, s->dead_l + (size_t)run * MS, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lnw) e = cudaMemcpy(lnw, s->dead_lw + (size_t)run * MS, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (prev >= 0) cudaSetDevice(prev);
+    return (int)e;
+}
+
+int nf_ns_stats(const nf_sampler *s, int32_t *lock_iters, int64_t *launches)
+{
+    if (!s) return NF_EINVAL;
+    if (lock_iters) *lock_iters = s->lock_iters;
+    if (launches) *launches = s->launches;
+    return NF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+"""Batched nested sampling: host wrapper of ``nf_ns_*`` (include/nestfit_b200.h)
+and the drop-in ``run_multinest`` / ``Dumper`` pair of the reference
+(nestfit/core/core.pyx:564-609,627-687,727-823).
+
+The sampler itself (proposal, prior transform, fused likelihood, accept/replace,
+evidence accumulation) runs on the device; this module sizes buffers, launches
+the run and packages results in the reference's result contract.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import NsConfig
+
+_VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
+_lib.register("nf_ns_create", [_VP, _VP, _I, _I, C.POINTER(NsConfig), _I64, _VP, _VP, C.POINTER(_VP)])
+_lib.register("nf_ns_run", [_VP])
+_lib.register("nf_ns_free", [_VP])
+_lib.register("nf_ns_results", [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP])
+_lib.register("nf_ns_posterior", [_VP, _I64, C.c_int32, _VP, _VP, _VP])
+_lib.register("nf_ns_stats", [_VP, C.POINTER(C.c_int32), C.POINTER(_I64)])
+
+# quantiles / labels written per run by the reference (core.pyx:585-594)
+MARG_QUANTILES = np.array([
+    0.00, 0.01, 0.10, 0.25, 0.50, 0.75, 0.90, 0.99, 1.00,
+    1.58655254e-1, 0.84134475,
+    2.27501319e-2, 0.97724987,
+    1.34989803e-3, 0.99865010,
+])
+MARG_COLS = ['min', 'p01', 'p10', 'p25', 'p50', 'p75', 'p90', 'p99', 'max',
+             '1s_lo', '1s_hi', '2s_lo', '2s_hi', '3s_lo', '3s_hi']
+
+
+class NestedSamplingBatch:
+    """Lock-step nested sampling of ``n_run`` (pixel, ncomp) fits on one GPU."""
+
+    def __init__(self, block, utrans, ncomp, pix_ids=None, nlive=100, tol=1.0, efr=0.3, n_prop=32, seed=1,
+                 max_iter=1_000_000, max_samples=None, cold=False, lte=False, method='auto', walks=0):
+        """method: 'auto' = ellipsoidal rejection sampling that hands a run over to a
+        constrained random walk once its acceptance stalls; 'ellipsoid' / 'rwalk' force one.
+        walks: random-walk steps per new point (0 = 20 + ndim)."""
+        lib = _lib.load()
+        self.block, self.utrans, self.ncomp = block, utrans, int(ncomp)
+        if pix_ids is None:
+            pix_ids = np.arange(block.n_pix)
+        self.pix_ids = np.ascontiguousarray(pix_ids, dtype=np.int32)
+        self.n_run = int(self.pix_ids.size)
+        self.nlive = np.ascontiguousarray(np.broadcast_to(np.asarray(nlive, dtype=np.int32), (self.n_run,)))
+        self.ndim = block.n_model * self.ncomp
+        nlive_max = int(self.nlive.max())
+        if max_samples is None:
+            max_samples = 64 * nlive_max
+        if seed is None or seed < 0:       # reference default seed=-1 means "from the clock" (core.pyx:731)
+            seed = int(np.random.SeedSequence().generate_state(1)[0])
+        self.cfg = NsConfig(nlive_max=nlive_max, n_prop=int(n_prop), max_iter=int(min(max_iter, 2**31 - 1)),
+                            max_samples=int(max_samples), bound_update_interval=int(walks),
+                            flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method], tol=float(tol),
+                            efr=float(efr), seed=int(seed))
+        flags = (_lib.NF_FLAG_COLD if cold else 0) | (_lib.NF_FLAG_LTE if lte else 0)
+        out = C.c_void_p()
+        _lib.check(lib.nf_ns_create(block.handle, utrans.handle(block.device), self.ncomp, flags,
+                                    C.byref(self.cfg), self.n_run, _lib.ptr(self.pix_ids), _lib.ptr(self.nlive),
+                                    C.byref(out)), "nf_ns_create")
+        self.handle = out
+        self._results = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().nf_ns_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self):
+        lib = _lib.load()
+        _lib.check(lib.nf_ns_run(self.handle), "nf_ns_run")
+        R, D = self.n_run, self.ndim
+        res = dict(lnZ=np.empty(R), lnZ_err=np.empty(R), max_loglike=np.empty(R),
+                   n_samples=np.empty(R, dtype=np.int32), n_iter=np.empty(R, dtype=np.int32),
+                   n_evals=np.empty(R, dtype=np.int64), bestfit=np.empty((R, D)), mapfit=np.empty((R, D)))
+        _lib.check(lib.nf_ns_results(self.handle, _lib.ptr(res["lnZ"]), _lib.ptr(res["lnZ_err"]),
+                                     _lib.ptr(res["max_loglike"]), _lib.ptr(res["n_samples"]),
+                                     _lib.ptr(res["n_iter"]), _lib.ptr(res["n_evals"]), _lib.ptr(res["bestfit"]),
+                                     _lib.ptr(res["mapfit"])), "nf_ns_results")
+        it, ln = C.c_int32(), C.c_int64()
+        lib.nf_ns_stats(self.handle, C.byref(it), C.byref(ln))
+        res["lock_iters"], res["launches"] = it.value, ln.value
+        res["truncated"] = res["n_samples"] >= self.cfg.max_samples
+        self._results = res
+        return res
+
+    @property
+    def results(self):
+        if self._results is None:
+            self.run()
+        return self._results
+
+    def posterior(self, run):
+        """(n_samples, ndim + 2) float64: physical parameters, lnL, posterior weight
+        (MultiNest's `posterior` array convention; weights sum to 1)."""
+        res = self.results
+        n = int(res["n_samples"][run])
+        th = np.empty((n, self.ndim), dtype=np.float32)
+        lnl = np.empty(n)
+        lnw = np.empty(n)
+        _lib.check(_lib.load().nf_ns_posterior(self.handle, run, n, _lib.ptr(th), _lib.ptr(lnl), _lib.ptr(lnw)),
+                   "nf_ns_posterior")
+        w = np.exp(lnl + lnw - res["lnZ"][run])
+        return np.concatenate([th.astype(np.float64), lnl[:, None], w[:, None]], axis=1)
+
+    def products(self, run, null_lnZ, n_chan_tot):
+        """Attributes and datasets the reference's dumper writes for one run
+        (core.pyx:645-687), as two dicts."""
+        res = self.results
+        post = self.posterior(run)
+        k = float(self.ndim)
+        n = float(n_chan_tot)
+        maxL = float(res["max_loglike"][run])
+        nullL = float(null_lnZ)
+        aic = 2 * k - 2 * maxL
+        null_aic = 2 * k - 2 * nullL
+        attrs = {
+            'ncomp': self.ncomp, 'null_lnZ': nullL, 'n_chan_tot': int(n_chan_tot),
+            'n_samples': int(res["n_samples"][run]), 'n_live': int(self.nlive[run]), 'n_params': self.ndim,
+            'global_lnZ': float(res["lnZ"][run]), 'global_lnZ_err': float(res["lnZ_err"][run]),
+            'max_loglike': maxL, 'marg_cols': MARG_COLS, 'marg_quantiles': MARG_QUANTILES,
+            'BIC': np.log(n) * k - 2 * maxL, 'AIC': aic, 'AICc': aic + (2 * k**2 + 2 * k) / (n - k - 1),
+            'null_BIC': np.log(n) * k - 2 * nullL, 'null_AIC': null_aic,
+            'null_AICc': null_aic + (2 * k**2 + 2 * k) / (n - k - 1),
+            # extras (not in the reference): sampler bookkeeping
+            'n_iter': int(res["n_iter"][run]), 'n_evals': int(res["n_evals"][run]),
+        }
+        dsets = {
+            'posteriors': post.astype('float32'),
+            # unweighted quantiles over all rows, mirroring core.pyx:596-598
+            'marginals': np.quantile(post[:, :-2], MARG_QUANTILES, axis=0),
+            'marginals_weighted': weighted_quantiles(post[:, :-2], post[:, -1], MARG_QUANTILES),
+            'bestfit_params': res["bestfit"][run].copy(),
+            'map_params': res["mapfit"][run].copy(),
+        }
+        return attrs, dsets
+
+
+def weighted_quantiles(x, w, q):
+    """Posterior-weighted quantiles per column (an addition: the reference's
+    `marginals` ignores the importance weights)."""
+    out = np.empty((len(q), x.shape[1]))
+    for j in range(x.shape[1]):
+        o = np.argsort(x[:, j])
+        cw = np.cumsum(w[o])
+        cw /= cw[-1]
+        out[:, j] = np.interp(q, cw, x[o, j])
+    return out
+
+
+class Dumper:
+    """Result sink with the reference's interface (core.pyx:564-609): writes run
+    attributes and datasets into an h5py-like group."""
+
+    def __init__(self, group, no_dump=False):
+        self.group = group
+        self.no_dump = no_dump
+        self.n_calls = 0
+        self.n_samples = -1
+        self.quantiles = MARG_QUANTILES
+        self.marginal_cols = MARG_COLS
+
+    def calc_marginals(self, posteriors):
+        return np.quantile(posteriors[:, :-2], self.quantiles, axis=0)
+
+    def flush(self):
+        f = getattr(self.group, "file", None)
+        if f is not None:
+            f.flush()
+
+    def append_attributes(self, **kwargs):
+        for name, value in kwargs.items():
+            self.group.attrs[name] = value
+
+    def append_datasets(self, **kwargs):
+        for name, data in kwargs.items():
+            self.group.create_dataset(name, data=data)
+
+
+def run_multinest(runner, dumper, IS=False, mmodal=True, ceff=False, nlive=400, tol=0.5, efr=0.3, nClsPar=None,
+                  maxModes=100, updInt=10, Ztol=-1e90, root='results', seed=-1, pWrap=None, fb=False,
+                  resume=False, initMPI=False, outfile=False, logZero=-1e100, maxiter=int(1e6), n_prop=32):
+    """Drop-in for the reference's ``run_multinest`` (core.pyx:727-823): fits the
+    runner's pixel with the batched device sampler (one run), sets
+    ``runner.run_lnZ`` and writes the reference's products through ``dumper``.
+    MultiNest-only switches (IS, mmodal, ceff, nClsPar, maxModes, updInt, Ztol,
+    pWrap, fb, resume, initMPI, outfile, logZero, root) are accepted and ignored."""
+    assert runner.ndim > 0
+    assert nlive > 0
+    assert tol > 0
+    assert 0 < efr <= 1
+    assert maxModes > 0
+    assert updInt > 0
+    assert Ztol is not None and np.isfinite(Ztol)
+    assert logZero is not None and np.isfinite(logZero)
+    assert maxiter >= 0
+    if nClsPar is not None and nClsPar > runner.n_params:
+        raise ValueError('Number of clustering parameters must be less than total.')
+    ns = NestedSamplingBatch(runner._block, runner.utrans, runner.ncomp, pix_ids=[0], nlive=nlive, tol=tol, efr=efr,
+                             n_prop=n_prop, seed=seed, max_iter=maxiter,
+                             cold=getattr(runner, "cold", False), lte=getattr(runner, "lte", False))
+    res = ns.run()
+    runner.run_lnZ = float(res["lnZ"][0])
+    if dumper is not None and not dumper.no_dump:
+        attrs, dsets = ns.products(0, runner.null_lnZ, runner.n_chan_tot)
+        dumper.append_attributes(**attrs)
+        dumper.append_datasets(**dsets)
+    dumper_calls = getattr(dumper, "n_calls", 0)
+    if dumper is not None:
+        dumper.n_calls = dumper_calls + 1
+        dumper.n_samples = int(res["n_samples"][0])
+    ns.close()
+    return res
