@@ -1,0 +1,53 @@
+"""GPU test of the cube path: CubeFitter.fit_cube on a small synthetic cube,
+ncomp escalation (main.py:450-469), NaN-pixel skipping (main.py:438-441) and the
+store layout (docs/store_spec.rst)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fit_cube_small(nb, tmp_path):
+    from nestfit_b200.synth import make_synth_stack
+    from nestfit_b200.store import HdfStore
+    from nestfit_b200.models import ammonia
+    ut = nb.get_irdc_priors()
+    ncomp_map = np.zeros((6, 4), dtype=int)
+    ncomp_map[2:4] = 1
+    ncomp_map[4:] = 2
+    stack = make_synth_stack((6, 4), ut, ncomp_map=ncomp_map, n_chan=400, dv=0.158, noise=0.1, seed=3)
+    # deterministic, well separated truths so the expected nbest is unambiguous
+    blk = nb.PixelBlock("ammonia", [c.xarr for c in stack.cubes], np.zeros((1, 2, 400), np.float32), 1.0,
+                        trans_ids=[1, 2])
+    t1 = np.array([[0.3, 14.0, 6.0, 14.6, 0.45, 0.0]])
+    t2 = np.array([[-1.5, 1.5, 12, 15, 5, 6, 14.6, 14.8, 0.35, 0.5, 0, 0]], dtype=float)
+    rng = np.random.default_rng(8)
+    for (lo, hi), t, nc in (((2, 4), t1, 1), ((4, 6), t2, 2)):
+        clean = blk.predict(t, nc)[0]
+        for c in (0, 1):
+            stack.cubes[c].data[lo:hi] = clean[c] + rng.normal(0, 0.1, (hi - lo, 4, 400))
+    stack.cubes[0].data[0, 0, 10] = np.nan                 # a blanked pixel
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=2, mn_kwargs={'nlive': 120}, n_prop=32,
+                           lnZ_thresh=11, seed=5)
+    res = fitter.fit_cube(str(tmp_path / 'cube'), nproc=1)[0]
+    nbest = res['nbest'].reshape(6, 4)
+    assert nbest[0, 0] == -1                                # NaN pixel skipped
+    assert np.all(nbest[:2].ravel()[1:] == 0)               # noise only
+    assert np.all(nbest[2:4] == 1) and np.all(nbest[4:] == 2)
+    # two-component fits were only attempted where one component was significant
+    assert np.isnan(res['lnZ'][:8, 2]).all() and np.isfinite(res['lnZ'][8:, 2]).all()
+    store = HdfStore(str(tmp_path / 'cube'))
+    assert store.hdf.attrs['n_max_components'] == 2 and store.hdf.attrs['lnZ_threshold'] == 11
+    assert store.hdf.attrs['model_name'] == 'ammonia' and store.hdf.attrs['naxis1'] == 6
+    groups = list(store.iter_pix_groups())
+    assert len(groups) == 23
+    g = store.hdf['/pix/5/3']
+    assert g.attrs['nbest'] == 2 and g.attrs['i_lon'] == 5 and '1' in g and '2' in g
+    run = g['2']
+    assert run.attrs['ncomp'] == 2 and run.attrs['n_params'] == 12 and run['marginals'].shape == (15, 12)
+    assert run['posteriors'].shape == (run.attrs['n_samples'], 14)
+    assert '2' not in store.hdf['/pix/0/1']
+    # fitted velocities of the 2-component pixels recover the truth ordering
+    v = run['bestfit_params'][:2]
+    assert abs(v[0] + 1.5) < 0.2 and abs(v[1] - 1.5) < 0.2
+    store.close()

@@ -1,0 +1,126 @@
+"""CPU tests of the host-side logic around the hot path: store tree, cube/stack
+array contract, pixel-block partitions and the world_size-2 (gloo) multi-rank path."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_memgroup_tree_and_persistence(tmp_path, nb):
+    from nestfit_b200.store import MemGroup
+    g = MemGroup()
+    p = g.require_group('/pix/3/4')
+    s = p.create_group('1')
+    s.attrs['ncomp'] = 1
+    s.attrs['marg_quantiles'] = np.arange(3.0)
+    s.create_dataset('posteriors', data=np.ones((4, 8), dtype='f4'))
+    with pytest.raises(ValueError):
+        p.create_group('1')            # the reference's create_group raises on re-fit (main.py:454)
+    assert '/pix/3/4/1' in g and '1' in p and '2' not in p
+    g.save(tmp_path / 't.npz')
+    h = MemGroup.load(tmp_path / 't.npz')
+    assert h['/pix/3/4/1'].attrs['ncomp'] == 1
+    np.testing.assert_array_equal(h['/pix/3/4/1'].attrs['marg_quantiles'], np.arange(3.0))
+    assert h['pix/3/4/1/posteriors'].dtype == np.float32 and h['pix/3/4/1/posteriors'].shape == (4, 8)
+
+
+def test_hdfstore_layout_and_links(tmp_path, nb):
+    from nestfit_b200.store import HdfStore
+    from nestfit_b200.models import ammonia
+    store = HdfStore(str(tmp_path / 'run'), nchunks=2)
+    assert store.store_dir.name == 'run.store' and len(store.chunk_paths) == 2
+    store.insert_model_metadata(ammonia.AmmoniaRunner)
+    assert store.hdf.attrs['model_name'] == 'ammonia' and store.hdf.attrs['n_params'] == 6
+    for i, lon in enumerate((0, 1)):
+        root = store.open_chunk(i)
+        g = root.require_group(f'/pix/{lon}/5')
+        g.attrs['nbest'] = i
+        g.create_group('1').attrs['global_lnZ'] = -1.0 * i
+        store.close_chunk(i, root)
+    store.link_files()
+    assert sorted(g.attrs['nbest'] for g in store.iter_pix_groups()) == [0, 1]
+    assert store.find_first_valid_group().attrs['global_lnZ'] in (0.0, -1.0)
+    store.close()
+    again = HdfStore(str(tmp_path / 'run'))
+    assert again.nchunks == 2 and again.model is ammonia
+    again.close()
+
+
+def test_cube_stack_contract(nb):
+    rng = np.random.default_rng(0)
+    x = np.linspace(2.369e10, 2.3695e10, 50)
+    cube = nb.DataCube.from_arrays(rng.normal(size=(4, 3, 50)), x[::-1].copy(), 0.35, trans_id=1)   # descending axis in
+    assert cube.xarr[1] > cube.xarr[0] and cube.shape == (4, 3, 50) and cube.spatial_shape == (4, 3)
+    noise = nb.NoiseMap(np.full((3, 4), 0.2))        # image (lat, lon) order -> transposed (main.py:41-44)
+    cube2 = nb.DataCube.from_arrays(rng.normal(size=(4, 3, 50)), x, noise, trans_id=2)
+    stack = nb.CubeStack([cube, cube2])
+    spec_data, has_nans = stack.get_spec_data(1, 2)
+    assert not has_nans and len(spec_data) == 2 and spec_data[1][3] == 2 and spec_data[0][2] == 0.35
+    assert stack.get_max_snr(1, 2) > 0
+    cube.data[0, 0, 3] = np.nan
+    assert stack.get_spec_data(0, 0)[1]
+    data, nz, valid = stack.block_arrays(np.array([0, 1]), np.array([0, 2]))
+    assert data.shape == (2, 2, 50) and nz.shape == (2, 2) and list(valid) == [False, True]
+    assert nb.NoiseMapUniform(0.35).get_noise(0, 0) == 0.35      # reference test_main.py:32-35
+
+
+def test_partitions(nb):
+    from nestfit_b200.parallel import block_bounds
+    idx = nb.get_multiproc_indices((5, 3), 2)          # reference row striping (main.py:565-571)
+    assert list(idx[0][0]) == [0, 0, 0, 2, 2, 2, 4, 4, 4] and list(idx[1][0]) == [1, 1, 1, 3, 3, 3]
+    blocks = nb.get_block_indices((5, 3), 4)
+    lon = np.concatenate([b[0] for b in blocks])
+    lat = np.concatenate([b[1] for b in blocks])
+    assert sorted(zip(lon, lat)) == [(i, j) for i in range(5) for j in range(3)]
+    assert all(np.all(np.diff(b[0] * 3 + b[1]) == 1) for b in blocks if b[0].size > 1)   # contiguous
+    for n, w in ((10, 3), (7, 8), (1024, 8)):
+        bb = block_bounds(n, w)
+        assert bb[0][0] == 0 and bb[-1][1] == n and all(a[1] == b[0] for a, b in zip(bb, bb[1:]))
+        sizes = [b - a for a, b in bb]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, %r)
+    from nestfit_b200.parallel import init_distributed, my_block, gather_blocks, max_over_ranks, rank_info
+    rank, local_rank, world = rank_info()
+    dist = init_distributed("gloo")
+    n_pix = 37
+    a, b = my_block(n_pix, rank, world)
+    # stand-in for the per-rank fit: lnZ of pixel i is -i, nbest is i %% 3
+    lnz = -np.arange(a, b, dtype=np.float64)[:, None] * np.ones((1, 3))
+    nbest = (np.arange(a, b) %% 3).astype(np.int64)
+    full_lnz = gather_blocks(lnz, n_pix, dist)
+    full_nb = gather_blocks(nbest, n_pix, dist)
+    t = max_over_ranks(1.0 + rank, dist)
+    dist.barrier()
+    if rank == 0:
+        assert full_lnz.shape == (n_pix, 3) and np.array_equal(full_lnz[:, 0], -np.arange(n_pix))
+        assert np.array_equal(full_nb, np.arange(n_pix) %% 3)
+        assert t == float(world)
+        print("GLOO_OK", world)
+    dist.destroy_process_group()
+''')
+
+
+def test_two_rank_gloo_partition_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % str(ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "GLOO_OK 2" in res.stdout
