@@ -161,8 +161,9 @@ struct __align__(32) LineRec {
 
 // Per-warp scratch in shared memory.
 template <int NC>
-struct __align__(16) WarpScratch {
-    LineRec line[NC][NF_MAX_LINES];
+struct __align__(32) WarpScratch {
+    LineRec line[NC][NF_MAX_LINES + 1];    // +1: the pair loop may touch one record past a run
+    uint4 tab[32];                         // per chunk: (first record offset | pair count << 16) per component
     float4 amp[NC][NF_MAX_SPEC];           // {aL, bL, aR, bR} of T_B amplitude lines
     double tauT[NC][NF_MAX_SPEC];          // main-line optical depth
     double soc[NC], voc[NC];               // sigma / c_kms, voff / c_kms
@@ -204,6 +205,18 @@ __device__ __forceinline__ void line_term(float &tau, const LineRec *rec, float 
     const float t = fmaf(A.y, d0, A.z);
     const float e = ex2_approx(t * d0);        // 2^(-k2 (d0^2 - 2 phi d0)); 2^(-k2 phi^2) is in A.w
     masked_fma(tau, A.w, e, d0, Bw.x, Bw.y);
+}
+
+// Number of lanes whose (lane-sorted, ascending) key is <= g; lane 31 must hold a sentinel.
+__device__ __forceinline__ int count_le_sorted(int key, int g)
+{
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(NF_FULL, key, pos + step - 1);
+        if (v <= g) pos += step;
+    }
+    return pos;
 }
 
 // (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels J >= 3 and J = 0)
@@ -349,6 +362,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
             const float t0a = sm.t0a, t0b = sm.t0b;
             // ---- P3: per-line window + Gaussian coefficients, lanes <-> lines ----
             uint32_t lohi[NC];
+            int keyF[NC], keyE[NC];     // NH3: first chunk at which a line has ended / has started
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int nl = IS_NH3 ? sm.nlines : ncomp;
@@ -376,9 +390,25 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                 int lo = __double2int_rd((rel - cut) * inv_chan);
                 int hi = __double2int_rd((rel + cut) * inv_chan);
                 bool on = act && !(hi < 0 || lo > a.n_chan - 1);   // hyperfine.pyx:88
+                const bool below = act && hi < 0;
                 lo = max(lo, 0);
                 hi = min(hi, a.n_chan - 1);
+                const bool inband = on;
                 on = on && hi > lo;                                // loop j in [lo, hi)
+                if (IS_NH3) {
+                    // keys are ascending in the (frequency-sorted) line index: windows entirely below
+                    // the band have always ended, those above it (and padding lanes) never start
+                    const int big = 1 << 24;
+                    int E = below ? -big : (inband ? (lo >> 5) : big);
+                    int F = below ? -big : (inband ? (on ? ((hi - 1) >> 5) + 1 : (lo >> 5)) : big);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {             // running max keeps F sorted around empty windows
+                        const int v = __shfl_up_sync(NF_FULL, F, o);
+                        if (lane >= o) F = max(F, v);
+                    }
+                    keyE[c] = E;
+                    keyF[c] = max(F, E);
+                }
                 const double jc = rel * inv_chan;
                 const int Ri = __double2int_rn(jc);
                 const float phi = (float)(jc - (double)Ri);
@@ -396,6 +426,10 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                 }
                 sc.line[c][lane].a = A;
                 sc.line[c][lane].w = Bw;
+                if (lane == 0) {        // the record one past the table is a null line
+                    sc.line[c][NF_MAX_LINES].a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sc.line[c][NF_MAX_LINES].w = make_float2(0.f, 0.f);
+                }
                 lohi[c] = on ? ((uint32_t)lo | ((uint32_t)hi << 16)) : 0u;
             }
             __syncwarp();
@@ -411,6 +445,75 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
             if (have_data)
                 drow = (pix == pix0 ? sdata + s * a.n_pad : a.data + pix * a.pix_stride + (int64_t)s * a.n_pad) + lane;
             float acc = 0.0f;
+            if (IS_NH3) {
+              for (int sb = 0; sb < nchunks; sb += 32) {
+                // per-chunk dispatch table: lanes <-> chunks; the lines touching chunk g are the
+                // contiguous run [#ended(g), #started(g)) of the frequency-sorted records
+                {
+                    uint32_t ent[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int g = sb + lane;
+                        const int first = count_le_sorted(keyF[c], g);
+                        const int end = count_le_sorted(keyE[c], g);
+                        const int cnt = end - first;
+                        ent[c] = cnt > 0 ? ((uint32_t)(first * (int)sizeof(LineRec)) | ((uint32_t)((cnt + 1) >> 1) << 16)) : 0u;
+                    }
+                    __syncwarp();
+                    sc.tab[lane] = make_uint4(ent[0], ent[1], ent[2], ent[3]);
+                    __syncwarp();
+                }
+                const int cend = min(32, nchunks - sb);
+                float xj = (float)((sb << 5) + lane);
+                for (int cc = 0; cc < cend; ++cc, xj += 32.0f) {
+                    const int g = sb + cc;
+                    const uint4 e4 = sc.tab[cc];
+                    const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+                    float d = 0.0f;
+                    if (have_data) d = drow[g << 5];
+                    if ((e4.x | e4.y | e4.z | e4.w) == 0u) {   // no line of any component touches this chunk
+                        if (WRITE_PRED) {
+                            const int j = (g << 5) + lane;
+                            if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
+                        }
+                        acc = fmaf(d, d, acc);
+                        continue;
+                    }
+                    const float T0 = fmaf(t0b, xj, t0a);
+                    float m = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const uint32_t ec = ent[c];
+                        if (ec == 0u) continue;
+                        const LineRec *rec = reinterpret_cast<const LineRec *>(
+                            reinterpret_cast<const unsigned char *>(&sc.line[c][0]) + (ec & 0xffffu));
+                        int n2 = (int)(ec >> 16);
+                        float tau = 0.0f;
+                        // two records per trip; a trailing odd slot reads the next record, whose own
+                        // window test masks it off in this chunk
+#pragma unroll 1
+                        do {
+                            line_term(tau, rec, xj);
+                            line_term(tau, rec + 1, xj);
+                            rec += 2;
+                        } while (--n2 > 0);
+                        const float4 am = ampc[c];
+                        const float D = fmaxf(fmaf(am.y, xj, am.x), fmaf(am.w, xj, am.z));
+                        // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
+                        const float e1s = tau * (1.0f - 0.5f * tau * (1.0f - tau * (1.0f / 3.0f)));
+                        const float e1l = 1.0f - ex2_approx(-(float)NF_LOG2E * tau);
+                        const float e1 = fabsf(tau) < 0.03125f ? e1s : e1l;
+                        m = fmaf(T0 * D, e1, m);
+                    }
+                    if (WRITE_PRED) {
+                        const int j = (g << 5) + lane;
+                        if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = m;
+                    }
+                    const float r = d - m;
+                    acc = fmaf(r, r, acc);
+                }
+              }
+            } else {
             for (int sb = 0; sb < nchunks; sb += 32) {
                 uint32_t cm[NC], un[NC];
 #pragma unroll
@@ -443,36 +546,18 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                         acc = fmaf(d, d, acc);
                         continue;
                     }
-                    const float T0 = fmaf(t0b, xj, t0a);
                     float m = 0.0f;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         if (!((un[c] >> cc) & 1u)) continue;
                         uint32_t lm = __ballot_sync(NF_FULL, (cm[c] >> cc) & 1u);
                         float tau = 0.0f;
-                        if (IS_NH3) {
-                            // lines are sorted in frequency with equal widths: the set that touches
-                            // a chunk is a contiguous run [first, first + cnt)
-                            const int first = __ffs(lm) - 1, cnt = __popc(lm);
-                            const LineRec *rec = &sc.line[c][first];
-                            const LineRec *rend = rec + cnt;
-#pragma unroll 2
-                            for (; rec != rend; ++rec) line_term(tau, rec, xj);
-                            const float4 am = ampc[c];
-                            const float D = fmaxf(fmaf(am.y, xj, am.x), fmaf(am.w, xj, am.z));
-                            // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
-                            const float e1s = tau * (1.0f - 0.5f * tau * (1.0f - tau * (1.0f / 3.0f)));
-                            const float e1l = 1.0f - ex2_approx(-(float)NF_LOG2E * tau);
-                            const float e1 = fabsf(tau) < 0.03125f ? e1s : e1l;
-                            m = fmaf(T0 * D, e1, m);
-                        } else {
-                            while (lm) {
-                                const int i = __ffs(lm) - 1;
-                                lm &= lm - 1;
-                                line_term(tau, &sc.line[c][i], xj);
-                            }
-                            m += tau;
+                        while (lm) {          // components are unordered: walk the set bits
+                            const int i = __ffs(lm) - 1;
+                            lm &= lm - 1;
+                            line_term(tau, &sc.line[c][i], xj);
                         }
+                        m += tau;
                     }
                     if (WRITE_PRED) {
                         const int j = (g << 5) + lane;
@@ -481,6 +566,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                     const float r = d - m;
                     acc = fmaf(r, r, acc);
                 }
+            }
             }
             if (have_data) {
                 const double tot = warp_sum((double)acc);
