@@ -6,9 +6,12 @@
  *
  * A plan is
  *   - `n_dist` distributions (core.pyx:23-45 `Distribution`): for each one a
- *     `nf_dist_desc` plus four consecutive double tables of `stride` entries
- *     (xax, pdf, cdf, ppf; stride = size + 1, the extra slot repeats the last
- *     value so the reference's one-past-the-end read at u == 1 is defined);
+ *     `nf_dist_desc` plus NF_DIST_TABLES consecutive double tables of `stride`
+ *     entries (xax, pdf, cdf, ppf, S0, S1, S2; stride = size + 1, the extra slot
+ *     repeats the last value so the reference's one-past-the-end read at u == 1
+ *     is defined).  S_m[i] = sum_{k<=i} k^m (pdf[k]+pdf[k-1])/2 are prefix moments
+ *     of the trapezoid terms: they give the interval CDF that
+ *     `cdf_over_interval` (core.pyx:109-161) rebuilds per call in closed form;
  *   - `n_prior` prior records executed in order (core.pyx:474-476).  Records
  *     flagged NF_PRIOR_NESTED are not executed at top level; they are the
  *     "sigma prior" objects the Resolved* priors call first
@@ -35,6 +38,7 @@ enum {
 };
 
 #define NF_PRIOR_NESTED 1u
+#define NF_DIST_TABLES 7
 #define NF_PRIOR_MAX_COMP 10 /* core.pyx:398-400: n > 10 is a silent no-op */
 
 typedef struct nf_dist_desc {

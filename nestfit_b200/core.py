@@ -18,6 +18,7 @@ FWHM = 2.3548200450309493  # core.pyx:20
 (KIND_PLAIN, KIND_CONSTANT, KIND_DUPLICATE, KIND_ORDERED, KIND_SPACED, KIND_CENSEP,
  KIND_RESOLVED_CENSEP, KIND_RESOLVED_PLACEMENT) = range(8)
 FLAG_NESTED = 1
+N_DIST_TABLES = 7   # xax, pdf, cdf, ppf, S0, S1, S2 (include/nf_priors.h)
 
 
 class Distribution:
@@ -47,10 +48,18 @@ class Distribution:
         self.ppf = interpolate.UnivariateSpline(strict, xax, k=3, s=0)(u)
 
     def tables(self):
-        """xax, pdf, cdf, ppf each padded to size+1 (last value repeated)."""
+        """xax, pdf, cdf, ppf each padded to size+1 (last value repeated), followed by the
+        prefix moments S_m[i] = sum_{k<=i} k^m t_k of the trapezoid terms
+        t_k = (pdf[k] + pdf[k-1]) / 2 (m = 0, 1, 2) that let the device evaluate the
+        reference's interval CDF (core.pyx:109-161) in closed form."""
         def pad(a):
             return np.concatenate([a, a[-1:]])
-        return np.concatenate([pad(self.xax), pad(self.pdf), pad(self.cdf), pad(self.ppf)])
+        k = np.arange(self.size, dtype=np.float64)
+        t = np.zeros(self.size)
+        t[1:] = 0.5 * (self.pdf[1:] + self.pdf[:-1])
+        moments = [np.cumsum(t * k**m) for m in range(3)]
+        return np.concatenate([pad(self.xax), pad(self.pdf), pad(self.cdf), pad(self.ppf)] +
+                              [pad(m) for m in moments])
 
 
 class Prior:
@@ -204,7 +213,7 @@ class _Plan:
             dd[i] = DistDesc(size=d.size, stride=stride, offset=off, pad_=0, xmin=d.xmin, xmax=d.xmax,
                              dx=d.dx, du=d.du)
             chunks.append(t)
-            off += 4 * stride
+            off += N_DIST_TABLES * stride
         tables = np.ascontiguousarray(np.concatenate(chunks) if chunks else np.zeros(1), dtype=np.float64)
         pp = (PriorDesc * len(self.records))(*self.records)
         return pp, len(self.records), dd, n_d, tables

@@ -20,7 +20,7 @@
 namespace {
 
 struct DistView {
-    const double *xax, *pdf, *ppf;
+    const double *xax, *pdf, *ppf, *S0, *S1, *S2;
     int size;
     double xmin, xmax, dx, du;
 };
@@ -32,6 +32,9 @@ __device__ __forceinline__ DistView bind_dist(const nf_dist_desc *dd, const doub
     v.xax = tables + d.offset;
     v.pdf = v.xax + d.stride;
     v.ppf = v.xax + 3 * (int64_t)d.stride;
+    v.S0 = v.xax + 4 * (int64_t)d.stride;
+    v.S1 = v.xax + 5 * (int64_t)d.stride;
+    v.S2 = v.xax + 6 * (int64_t)d.stride;
     v.size = d.size; v.xmin = d.xmin; v.xmax = d.xmax; v.dx = d.dx; v.du = d.du;
     return v;
 }
@@ -90,6 +93,34 @@ __device__ double placement_draw(const DistView &v, double x_lo, double x_hi, in
         return 1.0 / slope * (u - c0) + v.xax[lo];
     }
 
+    if (sfact <= 2) {
+        // closed form through prefix moments: numerator of the rebuilt CDF at index i,
+        //   P(i) = sum_{k=i_lo+1}^{i} t_k ((i_hi - k) / D)^sfact
+        const double D = (double)(i_hi - i_lo), ih = (double)i_hi;
+        const double b0 = v.S0[i_lo], b1 = v.S1[i_lo], b2 = v.S2[i_lo];
+        auto P = [&](int i) -> double {
+            const double d0 = v.S0[i] - b0;
+            if (sfact == 0) return d0;
+            const double d1 = v.S1[i] - b1;
+            if (sfact == 1) return (ih * d0 - d1) / D;
+            const double d2 = v.S2[i] - b2;
+            return (ih * ih * d0 - 2.0 * ih * d1 + d2) / (D * D);
+        };
+        const double csum = P(i_hi - 1);
+        if (!(csum > 0.0)) return nan("");
+        if (u <= 0.0) u = 1e-64;
+        const double target = fmin(u, 1.0) * csum;   // u lies in (0, 1]
+        int lo = i_lo, hi = i_hi - 1;          // P(lo) = 0 < target <= P(hi) for u <= 1
+        double p_lo = 0.0, p_hi = csum;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            const double pm = P(mid);
+            if (pm < target) { lo = mid; p_lo = pm; } else { hi = mid; p_hi = pm; }
+        }
+        const double c_lo = p_lo / csum, c_hi = p_hi / csum;
+        const double slope = (c_hi - c_lo) / v.dx;
+        return 1.0 / slope * (u - c_lo) + v.xax[lo];
+    }
     const double inv_delta = 1.0 / (double)(i_hi - i_lo);
     // sweep 1: normalisation
     double csum = 0.0;
@@ -245,7 +276,7 @@ int nf_priors_create(int device, const nf_prior_desc *priors, int n_prior, const
     for (int k = 0; k < n_dist; ++k) {
         const nf_dist_desc &d = dists[k];
         if (d.size < 2 || d.stride < d.size + 1 || d.offset < 0 ||
-            (int64_t)d.offset + 4 * (int64_t)d.stride > n_tables || !(d.dx > 0.0) || !(d.du > 0.0))
+            (int64_t)d.offset + NF_DIST_TABLES * (int64_t)d.stride > n_tables || !(d.dx > 0.0) || !(d.du > 0.0))
             return NF_EINVAL;
     }
     for (int k = 0; k < n_prior; ++k) {

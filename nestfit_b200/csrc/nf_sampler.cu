@@ -166,12 +166,14 @@ __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32
 // ---- bounding ellipsoid of the live set (one CTA per active run) -----------
 __global__ void __launch_bounds__(128)
 ns_bounds_kernel(const int32_t *act, const int32_t *nlive_arr, const int32_t *it_arr, const double *live_u,
-                 double *bound, int nlive_max, int ndim, double efr)
+                 double *bound, int nlive_max, int ndim, double efr, const int32_t *mode, const int32_t *coh_step)
 {
     __shared__ double s_mean[NS_MAX_DIM];
     __shared__ double s_c[NS_MAX_DIM][NS_MAX_DIM + 1];
     __shared__ double s_red[128];
     const int r = act[blockIdx.x];
+    // a random-walk cohort keeps the metric it started with: rebuild only at cohort start
+    if (mode[r] == 1 && coh_step[r] != 0) return;
     const int nl = nlive_arr[r];
     const int tid = threadIdx.x, d = ndim;
     const double *U = live_u + (int64_t)r * nlive_max * d;
@@ -758,7 +760,8 @@ int nf_ns_run(nf_sampler *s)
         D.K = K; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
         D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
         D.lock = lock;
-        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->nlive, s->it, s->live_u, s->bound, NL, d, s->cfg.efr);
+        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->nlive, s->it, s->live_u, s->bound, NL, d, s->cfg.efr,
+                                                s->mode, s->coh_step);
         const int nc = n_act * K;
         ns_propose_kernel<<<(nc + 127) / 128, 128, 0, st>>>(D);
         rc = score(s, s->cand_th, s->cand_pix, K, nc, s->cand_l);

@@ -37,7 +37,7 @@ def test_prior_plan_packing(nb):
     assert kinds == [0, 7, 0, 0, 0, 1]
     assert pp[0].flags == 1 and pp[1].nested == 0 and pp[1].p_ix == 0 and pp[1].p_ix2 == 4
     assert abs(pp[1].value - 2.3548200450309493 * 1.2) < 1e-15
-    assert tables.size == 5 * 4 * 501
+    assert tables.size == 5 * 7 * 501
     assert ut.n_param == 6
 
 
