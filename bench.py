@@ -281,12 +281,18 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(times[0]), float(times[1])
 
+    cube_result = None
+    if args.cube_size > 0:
+        del d_params, d_lnl, flush
+        torch.cuda.empty_cache()
+        cube_result = run_cube_fit(nb, args, rank, world, dev, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     evals = float(B_TOTAL) * world
     value = evals * args.steps / (total_ms * 1e-3)
+    cube = cube_result
     e2e_value = evals * n_e2e / e2e_s
 
     # ---- roofline of the dominant (only) kernel --------------------------------
@@ -358,9 +364,45 @@ def run_ours(args):
             "max_abs_dlnL_vs_gpu": float(err.max()),
             "parity_ok": bool((err <= 1e-3 + 2e-6 * np.abs(lnl_cpu)).all()),
         }
+    if cube is not None:
+        line["cube_fit"] = cube
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_cube_fit(nb, args, rank, world, dev, dist):
+    """Secondary metric (BASELINE M2): pixels/s of a full evidence-selected cube fit.  Each rank
+    fits its own contiguous block of a (size*world) x size synthetic cube (weak scaling)."""
+    import torch
+    from nestfit_b200.synth import make_synth_stack
+    from nestfit_b200.models import ammonia
+    from nestfit_b200.parallel import gather_blocks, max_over_ranks, block_bounds
+    n = args.cube_size
+    ut = nb.get_irdc_priors()
+    shape = (n * world, n)
+    lon, lat = np.indices(shape)
+    ncomp_map = ((lon // max(1, n // 4)) + (lat // max(1, n // 4))) % 3       # 0..2 true components
+    stack = make_synth_stack(shape, ut, ncomp_map=ncomp_map, n_chan=N_CHAN, dv=DV, noise=NOISE, seed=77, device=dev)
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=2, lnZ_thresh=11,
+                           mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=32)
+    blocks = nb.get_block_indices(shape, world)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = fitter.fit_block(blocks[rank], device=dev)
+    torch.cuda.synchronize()
+    secs = max_over_ranks(time.perf_counter() - t0, dist, device=f"cuda:{dev}")
+    nbest = gather_blocks(res['nbest'].astype(np.int64), shape[0] * shape[1], dist, device=f"cuda:{dev}")
+    evals = max_over_ranks(float(res['n_evals']), dist, device=f"cuda:{dev}")
+    if rank != 0:
+        return None
+    agree = float((nbest.reshape(shape) == ncomp_map).mean())
+    return {"metric": "cube pixels/s fit (ncomp <= 2 evidence model selection)", "value": shape[0] * shape[1] / secs,
+            "unit": "pixels/s", "seconds": secs, "cube": [shape[0], shape[1], 2, N_CHAN], "scaling": "weak",
+            "nlive": "100 + 5*SNR", "tol": 1.0, "likelihood_evals_per_pixel_max_rank": evals / (n * n),
+            "nbest_matches_truth": agree}
 
 
 def _with_device(nb, dev):
@@ -463,6 +505,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cube-size", type=int, default=24,
+                    help="side of the per-GPU synthetic cube of the secondary cube-fit metric (0 = skip)")
     args = ap.parse_args()
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch one process per GPU (the driver does this itself)
