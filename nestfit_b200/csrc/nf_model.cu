@@ -159,14 +159,35 @@ struct __align__(32) LineRec {
     float2 pad;
 };
 
+// Two adjacent hyperfine lines, element-interleaved so that the packed FP32x2 pipeline
+// (FADD2 / FFMA2 / FMUL2) works on both at once: 48 bytes = three LDS.128.
+struct __align__(16) PairRec {
+    float4 a;   // {R0, R1, -k2_0, -k2_1}
+    float4 b;   // {2 k2 phi (0), (1), weight*2^(-k2 phi^2) (0), (1)}
+    float4 w;   // {lo-R (0), (1), hi-R (0), (1)}
+};
+#define NF_MAX_PAIRS 17     // pairs (2q+p, 2q+p+1) of up to 33 records (32 lines + a null line)
+
 // Per-warp scratch in shared memory.
+template <int NC, bool NH3>
+struct __align__(32) WarpScratch;
+
 template <int NC>
-struct __align__(32) WarpScratch {
-    LineRec line[NC][NF_MAX_LINES + 1];    // +1: the pair loop may touch one record past a run
-    uint4 tab[32];                         // per chunk: (first record offset | pair count << 16) per component
+struct __align__(32) WarpScratch<NC, true> {
+    // pair[c][p][q] holds lines (2q+p, 2q+p+1): a run of lines may start at either parity
+    PairRec pair[NC][2][NF_MAX_PAIRS];
+    uint4 tab[32];                         // per chunk: (first pair offset | pair count << 16) per component
     float4 amp[NC][NF_MAX_SPEC];           // {aL, bL, aR, bR} of T_B amplitude lines
     double tauT[NC][NF_MAX_SPEC];          // main-line optical depth
     double soc[NC], voc[NC];               // sigma / c_kms, voff / c_kms
+};
+
+template <int NC>
+struct __align__(32) WarpScratch<NC, false> {
+    LineRec line[NC][NF_MAX_LINES];
+    float4 amp[NC][NF_MAX_SPEC];
+    double tauT[NC][NF_MAX_SPEC];
+    double soc[NC], voc[NC];
 };
 
 __device__ __forceinline__ float warp_sum_f32(float v)
@@ -194,6 +215,52 @@ __device__ __forceinline__ void masked_fma(float &tau, float w, float e, float d
         "}\n"
         : "+f"(tau)
         : "f"(d0), "f"(dlo), "f"(dhi), "f"(w), "f"(e));
+}
+
+// ---- packed FP32x2 arithmetic (sm_100a FADD2 / FFMA2 / FMUL2) -----------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// Two windowed Gaussian terms (lines 2q+p and 2q+p+1) at channel coordinate xj (packed twice).
+// The record stores -R so that d0 = xj + (-R) is a single FADD2.
+__device__ __forceinline__ void pair_term(float &tau0, float &tau1, const PairRec *rec, uint64_t xj2)
+{
+    const float4 A = rec->a, B = rec->b, W = rec->w;
+    const uint64_t d2 = add2(xj2, pack2(A.x, A.y));                       // exact: integer-valued floats
+    const uint64_t t2 = fma2(pack2(A.z, A.w), d2, pack2(B.x, B.y));
+    const uint64_t a2 = mul2(t2, d2);
+    float d0, d1, a0, a1;
+    unpack2(d2, d0, d1);
+    unpack2(a2, a0, a1);
+    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+    masked_fma(tau0, B.z, e0, d0, W.x, W.z);
+    masked_fma(tau1, B.w, e1, d1, W.y, W.w);
 }
 
 // One windowed Gaussian term of line record (A, Bw) at channel coordinate xj.
@@ -241,11 +308,11 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float *sdata = reinterpret_cast<float *>(smem_raw + 128);
     const int data_floats = a.n_spec * a.n_pad;
-    WarpScratch<NC> *scr_all =
-        reinterpret_cast<WarpScratch<NC> *>(smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128);
+    typedef WarpScratch<NC, IS_NH3> Scratch;
+    Scratch *scr_all = reinterpret_cast<Scratch *>(smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpScratch<NC> &sc = scr_all[warp];
+    Scratch &sc = scr_all[warp];
 
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t b0 = (int64_t)blockIdx.x * tile;
@@ -424,11 +491,25 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                     Bw.x = (float)(lo - Ri);
                     Bw.y = (float)(hi - Ri);
                 }
-                sc.line[c][lane].a = A;
-                sc.line[c][lane].w = Bw;
-                if (lane == 0) {        // the record one past the table is a null line
-                    sc.line[c][NF_MAX_LINES].a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    sc.line[c][NF_MAX_LINES].w = make_float2(0.f, 0.f);
+                if constexpr (IS_NH3) {
+                    // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
+                    // of the other parity that starts one line earlier
+                    float *e0 = reinterpret_cast<float *>(&sc.pair[c][lane & 1][lane >> 1]);
+                    e0[0] = -A.x; e0[2] = A.y; e0[4] = A.z; e0[6] = A.w; e0[8] = Bw.x; e0[10] = Bw.y;
+                    if (lane > 0) {
+                        float *e1 = reinterpret_cast<float *>(&sc.pair[c][(lane - 1) & 1][(lane - 1) >> 1]);
+                        e1[1] = -A.x; e1[3] = A.y; e1[5] = A.z; e1[7] = A.w; e1[9] = Bw.x; e1[11] = Bw.y;
+                    } else {
+                        // line 32 (element 1 of the last odd pair) and pair (32, 33) are null lines
+                        float *z = reinterpret_cast<float *>(&sc.pair[c][1][15]);
+                        z[1] = 0.f; z[3] = 0.f; z[5] = 0.f; z[7] = 0.f; z[9] = 0.f; z[11] = 0.f;
+                        sc.pair[c][0][16].a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        sc.pair[c][0][16].b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        sc.pair[c][0][16].w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else {
+                    sc.line[c][lane].a = A;
+                    sc.line[c][lane].w = Bw;
                 }
                 lohi[c] = on ? ((uint32_t)lo | ((uint32_t)hi << 16)) : 0u;
             }
@@ -445,7 +526,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
             if (have_data)
                 drow = (pix == pix0 ? sdata + s * a.n_pad : a.data + pix * a.pix_stride + (int64_t)s * a.n_pad) + lane;
             float acc = 0.0f;
-            if (IS_NH3) {
+            if constexpr (IS_NH3) {
               for (int sb = 0; sb < nchunks; sb += 32) {
                 // per-chunk dispatch table: lanes <-> chunks; the lines touching chunk g are the
                 // contiguous run [#ended(g), #started(g)) of the frequency-sorted records
@@ -457,7 +538,8 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                         const int first = count_le_sorted(keyF[c], g);
                         const int end = count_le_sorted(keyE[c], g);
                         const int cnt = end - first;
-                        ent[c] = cnt > 0 ? ((uint32_t)(first * (int)sizeof(LineRec)) | ((uint32_t)((cnt + 1) >> 1) << 16)) : 0u;
+                        const int poff = ((first & 1) * NF_MAX_PAIRS + (first >> 1)) * (int)sizeof(PairRec);
+                        ent[c] = cnt > 0 ? ((uint32_t)poff | ((uint32_t)((cnt + 1) >> 1) << 16)) : 0u;
                     }
                     __syncwarp();
                     sc.tab[lane] = make_uint4(ent[0], ent[1], ent[2], ent[3]);
@@ -465,38 +547,40 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                 }
                 const int cend = min(32, nchunks - sb);
                 float xj = (float)((sb << 5) + lane);
-                for (int cc = 0; cc < cend; ++cc, xj += 32.0f) {
-                    const int g = sb + cc;
-                    const uint4 e4 = sc.tab[cc];
+                const float *dp = have_data ? drow + (sb << 5) : nullptr;
+                const uint4 *tp = sc.tab;
+                for (int cc = 0; cc < cend; ++cc, xj += 32.0f, dp += 32, ++tp) {
+                    const uint4 e4 = *tp;
                     const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
                     float d = 0.0f;
-                    if (have_data) d = drow[g << 5];
+                    if (have_data) d = *dp;
                     if ((e4.x | e4.y | e4.z | e4.w) == 0u) {   // no line of any component touches this chunk
                         if (WRITE_PRED) {
-                            const int j = (g << 5) + lane;
+                            const int j = ((sb + cc) << 5) + lane;
                             if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
                         }
                         acc = fmaf(d, d, acc);
                         continue;
                     }
                     const float T0 = fmaf(t0b, xj, t0a);
+                    const uint64_t xj2 = pack2(xj, xj);
                     float m = 0.0f;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const uint32_t ec = ent[c];
                         if (ec == 0u) continue;
-                        const LineRec *rec = reinterpret_cast<const LineRec *>(
-                            reinterpret_cast<const unsigned char *>(&sc.line[c][0]) + (ec & 0xffffu));
+                        const PairRec *rec = reinterpret_cast<const PairRec *>(
+                            reinterpret_cast<const unsigned char *>(&sc.pair[c][0][0]) + (ec & 0xffffu));
                         int n2 = (int)(ec >> 16);
-                        float tau = 0.0f;
-                        // two records per trip; a trailing odd slot reads the next record, whose own
-                        // window test masks it off in this chunk
+                        float tau0 = 0.0f, tau1 = 0.0f;
+                        // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
+                        // whose own window test masks it off in this chunk
 #pragma unroll 1
                         do {
-                            line_term(tau, rec, xj);
-                            line_term(tau, rec + 1, xj);
-                            rec += 2;
+                            pair_term(tau0, tau1, rec, xj2);
+                            ++rec;
                         } while (--n2 > 0);
+                        const float tau = tau0 + tau1;
                         const float4 am = ampc[c];
                         const float D = fmaxf(fmaf(am.y, xj, am.x), fmaf(am.w, xj, am.z));
                         // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
@@ -506,7 +590,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
                         m = fmaf(T0 * D, e1, m);
                     }
                     if (WRITE_PRED) {
-                        const int j = (g << 5) + lane;
+                        const int j = ((sb + cc) << 5) + lane;
                         if (j < a.n_chan) a.pred[(b * a.n_spec + s) * (int64_t)a.n_chan + j] = m;
                     }
                     const float r = d - m;
@@ -580,18 +664,18 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     if (!data_ready) mbar_wait(bar, 0);
 }
 
-template <int NC>
+template <int NC, bool NH3>
 static size_t like_smem_bytes(const NfLikeArgs &a)
 {
     size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
-    return 128 + data + sizeof(WarpScratch<NC>) * NF_WARPS_PER_CTA;
+    return 128 + data + sizeof(WarpScratch<NC, NH3>) * NF_WARPS_PER_CTA;
 }
 
 template <int NC, bool IS_NH3, bool WP, typename PT>
 static cudaError_t launch_one(const NfLikeArgs &a, cudaStream_t st)
 {
     auto kern = nf_like_kernel<NC, IS_NH3, WP, PT>;
-    size_t smem = like_smem_bytes<NC>(a);
+    size_t smem = like_smem_bytes<NC, IS_NH3>(a);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
