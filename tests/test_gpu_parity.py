@@ -157,6 +157,30 @@ def test_nh3_random_batch_vs_oracle(nb, ncomp, n_chan, dv):
     assert_lnl(blk.loglike(P[:vpp * n_pix], ncomp, vecs_per_pix=vpp), want2["lnL"])
 
 
+def test_nh3_wide_band_ortho_mix_and_flags(nb):
+    """More than 1024 channels (several dispatch super-blocks), a para + ortho transition pair with
+    a free ortho fraction, one spectrum only, and the cold / lte switches through the likelihood."""
+    rng = np.random.default_rng(77)
+    ut = nb.get_irdc_priors()
+    for trans, n_chan, dv in (((1, 3), 2500, 0.05), ((2,), 300, 0.2), ((1, 2, 3), 700, 0.1)):
+        xs = [orc.bench_axis(t, n_chan, dv) for t in trans]
+        for ncomp in (1, 3):
+            P = orc.prior_transform(ut.pack(), rng.uniform(size=(400, 6 * ncomp)), ncomp)
+            P = P[np.isfinite(P).all(axis=1)][:256]
+            P[:, 5 * ncomp:] = rng.uniform(0.05, 0.9, size=(P.shape[0], ncomp))       # ortho fraction
+            clean = orc.nh3_batch(xs, list(trans), P[:2], ncomp, want_pred=True)["pred"]
+            data = (clean + rng.normal(0, 0.1, clean.shape)).astype(np.float32)
+            pix = (np.arange(P.shape[0]) % 2).astype(np.int32)
+            blk = nb.PixelBlock("ammonia", xs, data, 0.1, trans_ids=list(trans))
+            for cold, lte in ((False, False), (True, False), (False, True), (True, True)):
+                want = orc.nh3_batch(xs, list(trans), P, ncomp, data=data.astype(np.float64),
+                                     noise=np.full((2, len(trans)), 0.1), pix_of_vec=pix, cold=cold, lte=lte,
+                                     want_pred=True)
+                assert_lnl(blk.loglike(P, ncomp, pix_of_vec=pix, cold=cold, lte=lte), want["lnL"])
+                assert_spectra(blk.predict(P[:64], ncomp, cold=cold, lte=lte), want["pred"][:64])
+            blk.close()
+
+
 def test_edge_cases(nb):
     rng = np.random.default_rng(5)
     ut, xs, data, noise = _random_problem(nb, rng, 2, 3, 1000, 0.07)

@@ -1,0 +1,28 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer."""
+import sys
+import numpy as np
+sys.path.insert(0, '.')
+import nestfit_b200 as nb
+from nestfit_b200.sampler import NestedSamplingBatch
+from oracle import oracle as orc
+rng = np.random.default_rng(0)
+ut = nb.get_irdc_priors()
+xs = [orc.bench_axis(1, 200, 0.3), orc.bench_axis(2, 200, 0.3)]
+for nc in (1, 2, 3, 4):
+    P = ut.transform_batch(rng.uniform(size=(96, 6 * nc)), nc)
+    P[~np.isfinite(P).all(axis=1)] = P[0]
+    blk = nb.PixelBlock("ammonia", xs, rng.normal(0, 0.1, (5, 2, 200)).astype(np.float32), 0.1, trans_ids=[1, 2])
+    pix = np.sort(rng.integers(0, 5, 96)).astype(np.int32)
+    l1 = blk.loglike(P, nc, pix_of_vec=pix)
+    pr = blk.predict(P[:7], nc)
+    assert np.isfinite(l1).all() and np.isfinite(pr).all()
+    if nc <= 2:
+        ns = NestedSamplingBatch(blk, ut, nc, nlive=40, tol=1.0, n_prop=8, seed=1, max_iter=150)
+        r = ns.run(); assert np.isfinite(r['lnZ']).all(); ns.posterior(0); ns.close()
+    blk.close()
+v = (np.arange(300) - 149.5) * 0.3
+x = np.sort(orc.NU[0] * (1 - v / orc.CKMS))
+Pg = np.concatenate([rng.uniform(-30, 30, (40, 5)), rng.uniform(0.3, 3, (40, 5)), rng.uniform(0.1, 4, (40, 5))], axis=1)
+gb = nb.PixelBlock("gaussian", [x], rng.normal(0, 0.1, (2, 1, 300)).astype(np.float32), 0.1, rest_freq=orc.NU[0])
+assert np.isfinite(gb.loglike(Pg, 5, vecs_per_pix=20)).all() and np.isfinite(gb.predict(Pg, 5)).all()
+print("sanitize run ok")
