@@ -7,7 +7,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libnestfit_b200.so"
-SOURCES = ["nf_model.cu", "nf_priors.cu", "nf_sampler.cu", "nf_peaks.cu", "nf_capi.cu"]
+SOURCES = ["nf_model.cu", "nf_nh3.cu", "nf_priors.cu", "nf_sampler.cu", "nf_peaks.cu", "nf_capi.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-shared", "-Xcompiler", "-fPIC", "-DNF_BUILD",

@@ -22,14 +22,12 @@
 #include <vector>
 
 #include "nf_internal.cuh"
+#include "nf_device.cuh"
 #include "../../include/nf_nh3_tables.h"
 
-#define NF_FULL 0xffffffffu
 #ifndef NF_MIN_CTAS
 #define NF_MIN_CTAS 3
 #endif
-#define NF_LOG2E 1.4426950408889634
-#define NF_HK (NF_H / NF_KB)
 
 // ---- device tables -------------------------------------------------------
 __device__ double g_line_freq[NF_NH3_NLINES_TOTAL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
@@ -72,58 +70,6 @@ cudaError_t nf_model_init_device_tables(int device)
     return cudaSuccess;
 }
 
-// ---- small device helpers -------------------------------------------------
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NF_FULL, v, o);
-    return v;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
 
 // 1/(exp(x)-1) exactly as the reference evaluates it (table lerp inside the
 // table domain, expm1 outside), hyperfine.pyx:23-45.  FP64.
@@ -139,18 +85,6 @@ __device__ double iemtex_ref(double x)
     return 1.0 / expm1(x);
 }
 
-// exp(-x) with FastExp's argument handling (float-rounded argument, zero from 32 up)
-__device__ __forceinline__ double fastexp_f64(double x)
-{
-    float xf = (float)x;
-    return (xf < 32.0f) ? exp(-(double)xf) : 0.0;
-}
-
-template <typename T>
-__device__ __forceinline__ double ld_param(const void *base, int64_t idx)
-{
-    return (double)__ldg(reinterpret_cast<const T *>(base) + idx);
-}
 
 // One hyperfine line of one (component, spectrum): 32 bytes, read with one LDS.128 + one LDS.64.
 struct __align__(32) LineRec {
@@ -190,12 +124,6 @@ struct __align__(32) WarpScratch<NC, false> {
     double soc[NC], voc[NC];
 };
 
-__device__ __forceinline__ float warp_sum_f32(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NF_FULL, v, o);
-    return v;
-}
 
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {
@@ -217,35 +145,6 @@ __device__ __forceinline__ void masked_fma(float &tau, float w, float e, float d
         : "f"(d0), "f"(dlo), "f"(dhi), "f"(w), "f"(e));
 }
 
-// ---- packed FP32x2 arithmetic (sm_100a FADD2 / FFMA2 / FMUL2) -----------------------
-__device__ __forceinline__ uint64_t pack2(float lo, float hi)
-{
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
-{
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 
 // Two windowed Gaussian terms (lines 2q+p and 2q+p+1) at channel coordinate xj (packed twice).
 // The record stores -R so that d0 = xj + (-R) is a single FADD2.
@@ -694,7 +593,7 @@ static cudaError_t launch_nc(const NfLikeArgs &a, cudaStream_t st)
     return wp ? launch_one<NC, IS_NH3, true, float>(a, st) : launch_one<NC, IS_NH3, false, float>(a, st);
 }
 
-cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st)
+cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st)
 {
     switch (a.ncomp) {
     case 1: return launch_nc<1, true>(a, st);

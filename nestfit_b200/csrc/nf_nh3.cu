@@ -1,0 +1,551 @@
+// Fused NH3 hyperfine synthesis + radiative transfer + chi-square kernel (sm_100a), v6.
+//
+// One warp scores one parameter vector against one pixel; lanes <-> channels in the
+// FP32 main loop (32-channel chunks).  Everything around the main loop is laid out so
+// that lanes are busy:
+//   S  set-up, batched over the warp's next few vectors: lanes <-> (vector, component,
+//      spectrum); partition function, main-line optical depth and the brightness
+//      amplitude in FP64                                   (ammonia.pyx:289-361)
+//   L  per (vector, spectrum): lanes <-> (component, hyperfine line), flattened; window
+//      [lo, hi) with the reference's floor rule in FP64    (hyperfine.pyx:68-96)
+//   T  per-chunk dispatch table: lanes <-> chunks; the lines touching a chunk are a
+//      contiguous run of the frequency-sorted records (counting + warp scan)
+//   M  main loop: two lines per trip in packed FP32x2 (FADD2/FFMA2), MUFU.EX2, one
+//      compare per line (windows are stored symmetric about their own midpoint), then
+//      the radiative transfer and the residual per chunk   (hyperfine.pyx:98-113,
+//      core.pyx:522-530)
+//
+// Arithmetic identities used (all exact up to FP32 rounding):
+//   tau_j = sum_i tau_main w_i exp(-k_i (j - c_i)^2) is accumulated as
+//   tp_j = -log2(e) tau_j = -sum_i 2^(L_i + (B_i - k2_i d) d),  d = j - R'_i (exact),
+//   with log2(log2(e) tau_main w_i) folded into L_i, so exp(-tau_j) = 2^tp_j.
+//   FastExp semantics (nestfit/core/fastexp.c:234-283): exp(-x) of the float-rounded
+//   argument -> MUFU.EX2; Taylor-3 branch below 2^-5 kept for 1 - exp(-tau).
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "nf_internal.cuh"
+#include "nf_device.cuh"
+#include "../../include/nf_nh3_tables.h"
+
+#define NH3_WARPS NF_WARPS_PER_CTA
+#define NH3_KEY_NEVER 30000     // chunk key of a line above the band
+
+// ---- device tables ---------------------------------------------------------
+__device__ double n_line_freq[NF_NH3_NLINES_TOTAL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
+__device__ float n_line_l2w[NF_NH3_NLINES_TOTAL];    // log2 of the tau weights  ammonia.pyx:168-228
+__device__ double n_iem_y[NF_IEM_SIZE];              // 1/(exp(x_k)-1)         hyperfine.pyx:19
+__constant__ double n_iem_xmin, n_iem_xmax, n_iem_step, n_iem_inv_dx;
+
+static const double hn_nu[NF_NH3_NTRANS] = NF_NH3_REST_FREQ_INIT;
+static const int hn_off[NF_NH3_NTRANS + 1] = NF_NH3_LINE_OFFSET_INIT;
+static const double hn_voff[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_VOFF_INIT;
+static const double hn_wt[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_WEIGHT_INIT;
+
+static cudaError_t nh3_init_device_tables()
+{
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e) return e;
+    static bool done[64] = {false};
+    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    double freq[NF_NH3_NLINES_TOTAL];
+    float l2w[NF_NH3_NLINES_TOTAL];
+    for (int t = 0; t < NF_NH3_NTRANS; ++t)
+        for (int i = hn_off[t]; i < hn_off[t + 1]; ++i) {
+            freq[i] = (1.0 - hn_voff[i] / NF_CKMS) * hn_nu[t];
+            l2w[i] = (float)std::log2(hn_wt[i]);
+        }
+    if ((e = cudaMemcpyToSymbol(n_line_freq, freq, sizeof(freq)))) return e;
+    if ((e = cudaMemcpyToSymbol(n_line_l2w, l2w, sizeof(l2w)))) return e;
+    // hyperfine.pyx:12-20: x = linspace(XMIN, XMAX, 1000), y = 1/(exp(x)-1)
+    std::vector<double> y(NF_IEM_SIZE);
+    const double lo = NF_H * 23.0e9 / NF_KB, hi = NF_H * 28.0e9 / NF_KB;
+    const double xmin = lo / 8.0, xmax = hi / 2.7;
+    const double step = (xmax - xmin) / (double)(NF_IEM_SIZE - 1);
+    const double x1 = xmin + step, inv_dx = 1.0 / (x1 - xmin);
+    for (int k = 0; k < NF_IEM_SIZE; ++k) {
+        const double x = (k == NF_IEM_SIZE - 1) ? xmax : xmin + (double)k * step;
+        y[k] = 1.0 / (std::exp(x) - 1.0);
+    }
+    if ((e = cudaMemcpyToSymbol(n_iem_y, y.data(), sizeof(double) * NF_IEM_SIZE))) return e;
+    if ((e = cudaMemcpyToSymbol(n_iem_xmin, &xmin, sizeof(double)))) return e;
+    if ((e = cudaMemcpyToSymbol(n_iem_xmax, &xmax, sizeof(double)))) return e;
+    if ((e = cudaMemcpyToSymbol(n_iem_step, &step, sizeof(double)))) return e;
+    if ((e = cudaMemcpyToSymbol(n_iem_inv_dx, &inv_dx, sizeof(double)))) return e;
+    if (device >= 0 && device < 64) done[device] = true;
+    return cudaSuccess;
+}
+
+// 1/(exp(x)-1) exactly as the reference evaluates it (table lerp inside the table
+// domain, expm1 outside), hyperfine.pyx:23-45.  FP64.
+__device__ double nh3_iemtex(double x)
+{
+    if (n_iem_xmin < x && x < n_iem_xmax) {
+        int k = (int)((x - n_iem_xmin) * n_iem_inv_dx);
+        k = min(k, NF_IEM_SIZE - 2);
+        const double xk = n_iem_xmin + (double)k * n_iem_step;
+        const double yk = n_iem_y[k], yk1 = n_iem_y[k + 1];
+        return (yk1 - yk) * n_iem_inv_dx * (x - xk) + yk;
+    }
+    return 1.0 / expm1(x);
+}
+
+// Two adjacent hyperfine lines of one (component, spectrum), element-interleaved for the
+// packed FP32x2 pipeline: 48 bytes = two LDS.128 + one LDS.64.
+struct __align__(16) Nh3Pair {
+    float4 a;   // {-R'_0, -R'_1, -k2_0, -k2_1}     R' = window midpoint (multiple of 1/2)
+    float4 b;   // {B_0, B_1, L_0, L_1}             B = 2 k2 phi', L = log2(log2e tau w) - k2 phi'^2
+    float4 h;   // {h_0, h_1, -, -}                 window <=> |j - R'| <= h
+};
+
+// Per-warp scratch: the pair records (capacity set at launch from the transitions in use)
+// followed by this fixed part.
+template <int NC>
+struct __align__(16) Nh3Scratch {
+    uint4 tab[36];                        // per chunk and component: smem address of the first pair | pairs << 18;
+                                          // doubles as the counting array cnt[NC][36] while the table is built
+    float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
+    double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
+    float tauL[32];                       // log2(log2(e) * tau_main)
+    short2 key[NC][32];                   // per line: first chunk, first chunk after its window
+};
+
+// (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels other than J = 1, 2)
+#define NH3_BK_F ((float)(NF_HK * NF_BROT))
+#define NH3_CK_F ((float)(NF_HK * (NF_CROT - NF_BROT)))
+
+// ---- S: batched set-up, lanes <-> (vector, component, spectrum) -----------------
+template <int NC, typename PT>
+__device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC> &sc, int64_t bb, int nb,
+                                             int lane)
+{
+    const int n_spec = a.n_spec;
+    const int ipv = NC * n_spec;
+    const int kk = lane / ipv;
+    const int r = lane - kk * ipv;
+    const int c = r / n_spec, s = r - c * n_spec;
+    const bool valid = kk < nb;
+    const int64_t pbase = (bb + (valid ? kk : 0)) * (6 * NC);
+    const NfSpecMeta &sm = a.spec[s];
+    const double voff = ld_param<PT>(a.params, pbase + 0 * NC + c);
+    double trot = ld_param<PT>(a.params, pbase + 1 * NC + c);
+    double tex = ld_param<PT>(a.params, pbase + 2 * NC + c);
+    const double ntot = ld_param<PT>(a.params, pbase + 3 * NC + c);
+    const double sigm = ld_param<PT>(a.params, pbase + 4 * NC + c);
+    const double orth = ld_param<PT>(a.params, pbase + 5 * NC + c);
+    if (a.cold)  // swift_convert, ammonia.pyx:280-286
+        trot = trot / (1.0 + (trot / 41.18) * log(1.0 + 0.6 * exp(-15.7 / trot)));
+    if (a.lte) tex = trot;                                              // ammonia.pyx:346-347
+    // partition function (ammonia.pyx:289-315): levels J = 1, 2 carry all but ~1e-3 of
+    // Q_para and are added in FP64; the others go through MUFU.EX2 in FP32, summed while
+    // any lane's level is inside FastExp's range (x < 32)
+    const int my_J = sm.J, my_para = sm.para;
+    const float itr = 1.0f / (float)trot;
+    float q32 = 0.0f;
+    for (int J = 0; J <= 50; ++J) {
+        if (J == 1 || J == 2) continue;
+        const float Jf = (float)J;
+        const float x = (NH3_BK_F * Jf * (Jf + 1.0f) + NH3_CK_F * Jf * Jf) * itr;
+        const bool live = x < 32.0f;
+        if (!__any_sync(NF_FULL, live && valid)) break;
+        const float lev = live ? (2.0f * Jf + 1.0f) * ex2_approx(-(float)NF_LOG2E * x) : 0.0f;
+        const bool ortho_J = (J % 3) == 0;
+        if (my_para ? !ortho_J : ortho_J) q32 += my_para ? lev : 2.0f * lev;
+    }
+    const double a1 = NF_HK * (2.0 * NF_BROT + (NF_CROT - NF_BROT));
+    const double a2 = NF_HK * (6.0 * NF_BROT + 4.0 * (NF_CROT - NF_BROT));
+    const double lev1 = 3.0 * fastexp_f64(a1 / trot);
+    const double lev2 = 5.0 * fastexp_f64(a2 / trot);
+    double zlev = my_J == 1 ? lev1 : lev2;
+    if (my_J > 2) {
+        const double J = (double)my_J;
+        zlev = (2.0 * J + 1.0) * fastexp_f64(NF_HK * (NF_BROT * J * (J + 1.0) + (NF_CROT - NF_BROT) * J * J) / trot);
+    }
+    const double qtot = my_para ? lev1 + lev2 + (double)q32 : (double)q32;
+    const double frac = my_para ? 1.0 - orth : orth;
+    const double pop = exp10(ntot) * frac * zlev / qtot;          // ammonia.pyx:353
+    const double e = exp(-sm.hnu_k / tex);                        // ammonia.pyx:354-357
+    const double tau_main = pop * sm.fracterm * ((1.0 - e) / (1.0 + e)) * (sm.width_c / sigm);
+    // T_B amplitude T0_j * (G(T0_j/tex) - tbg_j), hyperfine.pyx:106-113, as the max of two
+    // lines in j: the reference's G is a convex piecewise-linear table, so this reproduces
+    // the table lerp -- including a knot inside the band -- without per-channel look-ups.
+    const double nm1 = (double)(a.n_chan - 1);
+    const double xL = sm.T0_first / tex, xR = sm.T0_last / tex;
+    const double dxdj = (xR - xL) / nm1;
+    double aL, bL, aR, bR;
+    const bool inL = n_iem_xmin < xL && xL < n_iem_xmax;
+    const bool inR = n_iem_xmin < xR && xR < n_iem_xmax;
+    if (inL && inR) {
+        const int kL = min((int)((xL - n_iem_xmin) * n_iem_inv_dx), NF_IEM_SIZE - 2);
+        const int kR = min((int)((xR - n_iem_xmin) * n_iem_inv_dx), NF_IEM_SIZE - 2);
+        double xk = n_iem_xmin + (double)kL * n_iem_step;
+        double sl = (n_iem_y[kL + 1] - n_iem_y[kL]) * n_iem_inv_dx;
+        aL = n_iem_y[kL] + sl * (xL - xk);
+        bL = sl * dxdj;
+        xk = n_iem_xmin + (double)kR * n_iem_step;
+        sl = (n_iem_y[kR + 1] - n_iem_y[kR]) * n_iem_inv_dx;
+        aR = n_iem_y[kR] + sl * (xL - xk);
+        bR = sl * dxdj;
+    } else {
+        const double gL = nh3_iemtex(xL), gR = nh3_iemtex(xR);
+        aL = aR = gL;
+        bL = bR = (gR - gL) / nm1;
+    }
+    // fold T0_j = T0_first + (T0_last - T0_first) j / (N-1) into both lines (the j^2 term
+    // of the product is below 1e-8 of the amplitude): line through the end-channel values
+    const double pL0 = sm.T0_first * (aL - sm.tbg0);
+    const double pL1 = sm.T0_last * (aL + bL * nm1 - sm.tbg0 - sm.tbg1 * nm1);
+    const double pR0 = sm.T0_first * (aR - sm.tbg0);
+    const double pR1 = sm.T0_last * (aR + bR * nm1 - sm.tbg0 - sm.tbg1 * nm1);
+    if (valid) {
+        sc.amp[lane] = make_float4((float)pL0, (float)pR0, (float)((pL1 - pL0) / nm1), (float)((pR1 - pR0) / nm1));
+        sc.tauL[lane] = log2f((float)(tau_main * NF_LOG2E));
+        sc.soc[lane] = sigm / NF_CKMS;
+        sc.voc[lane] = voff / NF_CKMS;
+    }
+}
+
+// tp -= e for lanes whose channel lies inside the line's window, |d| <= h
+__device__ __forceinline__ void masked_sub(float &tp, float e, float d, float h)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .f32 ad;\n"
+        "abs.f32 ad, %2;\n"
+        "setp.le.f32 p, ad, %3;\n"
+        "@p sub.f32 %0, %0, %1;\n"
+        "}\n"
+        : "+f"(tp)
+        : "f"(e), "f"(d), "f"(h));
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+// Two windowed Gaussian terms (lines 2q+p and 2q+p+1) at channel coordinate xj (packed twice).
+__device__ __forceinline__ void nh3_pair_term(float &tp, uint32_t ra, uint64_t xj2)
+{
+    const float4 A = lds128(ra), B = lds128(ra + 16);
+    const float2 H = lds64(ra + 32);
+    const uint64_t d2 = add2(xj2, pack2(A.x, A.y));                        // exact: multiples of 1/2
+    const uint64_t t2 = fma2(pack2(A.z, A.w), d2, pack2(B.x, B.y));
+    const uint64_t a2 = fma2(t2, d2, pack2(B.z, B.w));
+    float d0, d1, a0, a1;
+    unpack2(d2, d0, d1);
+    unpack2(a2, a0, a1);
+    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+    masked_sub(tp, e0, d0, H.x);
+    masked_sub(tp, e1, d1, H.y);
+}
+
+// ---- the fused kernel ---------------------------------------------------------
+// WRITE_PRED = false: log-likelihood against the pixel's data (a.data, a.lnL);
+// WRITE_PRED = true : model spectra only (a.pred), no data are read.
+template <int NC, bool WRITE_PRED, typename PT>
+__global__ void __launch_bounds__(NF_THREADS, (NC <= 3 ? 4 : 3))
+nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *sdata = reinterpret_cast<float *>(smem_raw + 128);
+    const int data_floats = a.n_spec * a.n_pad;
+    typedef Nh3Scratch<NC> Scratch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // pair[c][p][q] holds lines (2q+p, 2q+p+1); npair pairs per parity
+    const int npair = a.npair;
+    const size_t warp_bytes = (size_t)NC * 2 * npair * sizeof(Nh3Pair) + sizeof(Scratch);
+    unsigned char *wbase = smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128 + warp * warp_bytes;
+    float *pairf = reinterpret_cast<float *>(wbase);
+    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + (size_t)NC * 2 * npair * sizeof(Nh3Pair));
+    uint32_t *cw = reinterpret_cast<uint32_t *>(sc.tab);   // cnt[c][g] = cw[c * 36 + g]
+    const uint32_t pair_addr = smem_u32(pairf);
+
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    const int64_t b0 = (int64_t)blockIdx.x * tile;
+    constexpr bool have_data = !WRITE_PRED;
+    int64_t pix0 = 0;
+    if (have_data) {
+        pix0 = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b0) : b0 / a.vecs_per_pix;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0)
+            tma_load_1d(sdata, a.data + pix0 * a.pix_stride, (uint32_t)(data_floats * 4), bar);
+    }
+    bool data_ready = !have_data;
+
+    const int n_spec = a.n_spec;
+    const int ipv = NC * n_spec;
+    const int nchunks = (a.n_chan + 31) >> 5;
+    // the warp's vectors: a contiguous slice of the tile, set up in batches of vb
+    const int vpw = (tile + NH3_WARPS - 1) / NH3_WARPS;
+    const int vb = min(32 / ipv, 8);
+    int64_t bw_end = b0 + (int64_t)(warp + 1) * vpw;
+    if (bw_end > b0 + tile) bw_end = b0 + tile;
+    if (bw_end > a.B) bw_end = a.B;
+
+    // FastExp's Taylor branch for 1 - exp(-tau), tau < 2^-5 (fastexp.c:265-270), in tp = -log2(e) tau
+    const float kC1 = -(float)NF_LN2, kC2 = -(float)(0.5 * NF_LN2 * NF_LN2),
+                kC3 = -(float)(NF_LN2 * NF_LN2 * NF_LN2 / 6.0);
+    const float kThr = -(float)(0.03125 * NF_LOG2E);
+
+    for (int64_t bb = b0 + (int64_t)warp * vpw; bb < bw_end; bb += vb) {
+        const int nb = (int)min((int64_t)vb, bw_end - bb);
+        nh3_setup_batch<NC, PT>(a, sc, bb, nb, lane);
+        __syncwarp();
+
+        for (int k = 0; k < nb; ++k) {
+            const int64_t b = bb + k;
+            int64_t pix = 0;
+            if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;
+            double lnl = 0.0;
+            for (int s = 0; s < n_spec; ++s) {
+                const NfSpecMeta &sm = a.spec[s];
+                // ---- L: line records, lanes <-> (component, line) flattened ----
+                for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
+                __syncwarp();
+                {
+                    const int NL = sm.nlines, nitems = NC * NL;
+                    const double nu_min = sm.nu_min, inv_chan = sm.inv_chan;
+                    for (int t0 = 0; t0 < nitems; t0 += 32) {
+                        const int t = t0 + lane;
+                        const bool act = t < nitems;
+                        int c = 0;
+                        if (NC > 1) c += t >= NL;
+                        if (NC > 2) c += t >= 2 * NL;
+                        if (NC > 3) c += t >= 3 * NL;
+                        int i = t - c * NL;
+                        if (!act) { c = 0; i = 0; }
+                        const int it = k * ipv + c * n_spec + s;
+                        const double f = n_line_freq[sm.line_off + i];
+                        const double w = sc.soc[it] * f;                 // hyperfine.pyx:71
+                        const double nucen = f - sc.voc[it] * f;         // hyperfine.pyx:72-73
+                        const double cut = 5.0 * fabs(w);                // sqrt(12.5 / (0.5 / w^2)), hyperfine.pyx:82
+                        const double rel = nucen - nu_min;
+                        // floor((nu_cen - nu_min -/+ cut) / nu_chan), hyperfine.pyx:83-87.  cvt.rmi saturates
+                        // and maps NaN to 0, so non-finite parameters end up with an empty window.
+                        int lo = __double2int_rd((rel - cut) * inv_chan);
+                        int hi = __double2int_rd((rel + cut) * inv_chan);
+                        const bool inband = !(hi < 0 || lo > a.n_chan - 1);   // hyperfine.pyx:88
+                        const bool below = hi < 0;
+                        lo = max(lo, 0);
+                        hi = min(hi, a.n_chan - 1);
+                        const bool on = inband && hi > lo;                    // loop j in [lo, hi)
+                        // chunk keys, ascending in the (frequency-sorted) line index.  An in-band line with an
+                        // empty window keeps a nominal one-channel extent so that both keys stay sorted.
+                        const int hi_n = max(hi, lo + 1);
+                        const int kE = below ? -1 : (inband ? (lo >> 5) : NH3_KEY_NEVER);
+                        const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 5) + 1 : NH3_KEY_NEVER);
+                        float mR = 0.f, mk2 = 0.f, Bq = 0.f, Lq = -INFINITY, hh = -1.0f;
+                        if (on) {
+                            const int r2 = lo + hi - 1;                       // twice the window midpoint
+                            const double jc = rel * inv_chan;
+                            const float phi = (float)(jc - 0.5 * (double)r2);
+                            const float sch = (float)(w * inv_chan);
+                            const float k2 = __fdividef(0.5f * (float)NF_LOG2E, sch * sch);
+                            mR = -0.5f * (float)r2;
+                            mk2 = -k2;
+                            Bq = 2.0f * k2 * phi;
+                            Lq = sc.tauL[it] + n_line_l2w[sm.line_off + i] - k2 * phi * phi;
+                            hh = 0.5f * (float)(hi - 1 - lo);
+                        }
+                        if (act) {
+                            sc.key[c][i] = make_short2((short)kE, (short)kF);
+                            atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u);          // table counts of super-block 0
+                            atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x10000u);
+                            // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
+                            // of the other parity that starts one line earlier
+                            float *pb = pairf + c * (2 * npair * 12);
+                            float *e0 = pb + ((i & 1) * npair + (i >> 1)) * 12;
+                            e0[0] = mR; e0[2] = mk2; e0[4] = Bq; e0[6] = Lq; e0[8] = hh;
+                            if (i > 0) {
+                                float *e1 = pb + (((i - 1) & 1) * npair + ((i - 1) >> 1)) * 12;
+                                e1[1] = mR; e1[3] = mk2; e1[5] = Bq; e1[7] = Lq; e1[9] = hh;
+                            }
+                            if (i == NL - 1) {   // the null line NL closes an odd run that ends at the last line
+                                e0[1] = 0.f; e0[3] = 0.f; e0[5] = 0.f; e0[7] = -INFINITY; e0[9] = -1.0f;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (!data_ready) { mbar_wait(bar, 0); data_ready = true; }
+
+                // amplitude lines of this spectrum: one float4 {intercept_L, intercept_R, slope_L, slope_R} per component
+                const uint32_t amp_addr = smem_u32(&sc.amp[k * ipv + s]);
+                // this pixel's row: the CTA's staged copy in shared memory when the vector belongs to
+                // the tile's pixel, else straight from HBM/L2 (generic pointer, one LD per chunk)
+                const float *drow = nullptr;
+                if (have_data)
+                    drow = (pix == pix0 ? sdata + s * a.n_pad : a.data + pix * a.pix_stride + (int64_t)s * a.n_pad) + lane;
+                float acc = 0.0f;
+                for (int sb = 0; sb < nchunks; sb += 32) {
+                    // ---- T: per-chunk dispatch table, lanes <-> chunks ----
+                    {
+                        if (sb > 0) {   // later super-blocks (n_chan > 1024): recount from the stored keys
+                            for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
+                            __syncwarp();
+                            const int NL = sm.nlines, nitems = NC * NL;
+                            for (int t0 = 0; t0 < nitems; t0 += 32) {
+                                const int t = t0 + lane;
+                                if (t < nitems) {
+                                    int c = 0;
+                                    if (NC > 1) c += t >= NL;
+                                    if (NC > 2) c += t >= 2 * NL;
+                                    if (NC > 3) c += t >= 3 * NL;
+                                    const int i = t - c * NL;
+                                    const short2 ky = sc.key[c][i];
+                                    atomicAdd(&cw[c * 36 + min(max((int)ky.x - sb, 0), 32)], 1u);
+                                    atomicAdd(&cw[c * 36 + min(max((int)ky.y - sb, 0), 32)], 0x10000u);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        uint32_t v[NC];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) v[c] = cw[c * 36 + lane];
+                        __syncwarp();
+                        uint32_t ent[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t u = __shfl_up_sync(NF_FULL, v[c], o);
+                                if (lane >= o) v[c] += u;
+                            }
+                            const int end = (int)(v[c] & 0xffffu), first = (int)(v[c] >> 16);
+                            const int cnt = end - first;
+                            const uint32_t addr = pair_addr + (uint32_t)(((c * 2 + (first & 1)) * npair + (first >> 1)) * (int)sizeof(Nh3Pair));
+                            ent[c] = cnt > 0 ? (addr | ((uint32_t)((cnt + 1) >> 1) << 18)) : 0u;
+                        }
+                        sc.tab[lane] = make_uint4(ent[0], ent[1], ent[2], ent[3]);
+                        __syncwarp();
+                    }
+                    // ---- M: main loop over the chunks of this super-block ----
+                    const int cend = min(32, nchunks - sb);
+                    float xj = (float)((sb << 5) + lane);
+                    const float *dp = have_data ? drow + (sb << 5) : nullptr;
+                    const uint4 *tp = sc.tab;
+                    for (int cc = 0; cc < cend; ++cc, xj += 32.0f, dp += 32, ++tp) {
+                        const uint4 e4 = *tp;
+                        const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+                        float d = 0.0f;
+                        if (have_data) d = *dp;
+                        if ((e4.x | e4.y | e4.z | e4.w) == 0u) {   // no line of any component touches this chunk
+                            if (WRITE_PRED) {
+                                const int j = ((sb + cc) << 5) + lane;
+                                if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
+                            }
+                            acc = fmaf(d, d, acc);
+                            continue;
+                        }
+                        const uint64_t xj2 = pack2(xj, xj);
+                        float m = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const uint32_t ec = ent[c];
+                            if (ec == 0u) continue;
+                            uint32_t ra = ec & 0x3ffffu;
+                            const uint32_t rend = ra + (ec >> 18) * (uint32_t)sizeof(Nh3Pair);
+                            float tpv = 0.0f;                            // -log2(e) * tau_j
+                            // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
+                            // whose own window test masks it off in this chunk
+#pragma unroll 1
+                            do {
+                                nh3_pair_term(tpv, ra, xj2);
+                                ra += (uint32_t)sizeof(Nh3Pair);
+                            } while (ra != rend);
+                            // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
+                            const float e1s = tpv * fmaf(tpv, fmaf(tpv, kC3, kC2), kC1);
+                            const float e1l = 1.0f - ex2_approx(tpv);
+                            const float e1 = tpv > kThr ? e1s : e1l;
+                            float aL, aR;
+                            const float4 am = lds128(amp_addr + (uint32_t)(c * n_spec) * 16u);   // {i_L, i_R, s_L, s_R}
+                            unpack2(fma2(pack2(am.z, am.w), xj2, pack2(am.x, am.y)), aL, aR);
+                            m = fmaf(fmaxf(aL, aR), e1, m);
+                        }
+                        if (WRITE_PRED) {
+                            const int j = ((sb + cc) << 5) + lane;
+                            if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = m;
+                        }
+                        const float r = d - m;
+                        acc = fmaf(r, r, acc);
+                    }
+                }
+                if (have_data) {
+                    const double tot = warp_sum((double)acc);
+                    lnl -= tot * __ldg(a.inv2s2 + pix * n_spec + s);
+                }
+                __syncwarp();
+            }
+            if (a.lnL && lane == 0) a.lnL[b] = lnl;
+        }
+        __syncwarp();
+    }
+    // a CTA whose warps all ran out of vectors must still drain the bulk copy
+    if (!data_ready) mbar_wait(bar, 0);
+}
+
+template <int NC>
+static size_t nh3_smem_bytes(const NfLikeArgs &a)
+{
+    const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
+    return 128 + data + ((size_t)NC * 2 * a.npair * sizeof(Nh3Pair) + sizeof(Nh3Scratch<NC>)) * NH3_WARPS;
+}
+
+template <int NC, bool WP, typename PT>
+static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
+{
+    NfLikeArgs a = a0;
+    int max_lines = 1;
+    for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
+    a.npair = (max_lines >> 1) + 1;     // lines 0..NL (NL = the null line) in pairs of either parity
+    auto kern = nf_nh3_kernel<NC, WP, PT>;
+    const size_t smem = nh3_smem_bytes<NC>(a);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    const int64_t grid = (a.B + tile - 1) / tile;
+    if (grid <= 0) return cudaSuccess;
+    kern<<<(unsigned)grid, NF_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int NC>
+static cudaError_t nh3_launch_nc(const NfLikeArgs &a, cudaStream_t st)
+{
+    const bool wp = a.pred != nullptr;
+    if (a.param_f64)
+        return wp ? nh3_launch_one<NC, true, double>(a, st) : nh3_launch_one<NC, false, double>(a, st);
+    return wp ? nh3_launch_one<NC, true, float>(a, st) : nh3_launch_one<NC, false, float>(a, st);
+}
+
+cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st);
+
+cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st)
+{
+    static const bool legacy = std::getenv("NF_NH3_LEGACY") != nullptr;
+    if (legacy) return nf_launch_nh3_legacy(a, st);
+    cudaError_t e = nh3_init_device_tables();
+    if (e) return e;
+    switch (a.ncomp) {
+    case 1: return nh3_launch_nc<1>(a, st);
+    case 2: return nh3_launch_nc<2>(a, st);
+    case 3: return nh3_launch_nc<3>(a, st);
+    case 4: return nh3_launch_nc<4>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
