@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 1
+#define NF_ABI_VERSION 2
 
 enum {
     NF_OK = 0,
@@ -162,6 +162,9 @@ typedef struct nf_ns_config {
     double tol;          /* `tol`: stop when ln(Z + Lmax X) - ln Z < tol               */
     double efr;          /* `efr`: target sampling efficiency (ellipsoid enlargement)  */
     uint64_t seed;       /* counter-based RNG seed: results are reproducible           */
+    int32_t n_prop_max;  /* most proposals a run may get per lock-step once few runs remain
+                            (rounded down to a multiple of n_prop; <= n_prop: fixed K)       */
+    int32_t target_batch; /* vectors per likelihood launch aimed at in that regime (0: 65536) */
 } nf_ns_config;
 
 /* pix_ids[n_run], nlive[n_run] are host arrays (nlive per run: main.py:445-447).

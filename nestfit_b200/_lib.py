@@ -40,7 +40,8 @@ class NsConfig(C.Structure):
     """Mirror of `nf_ns_config` (include/nestfit_b200.h)."""
     _fields_ = [("nlive_max", C.c_int32), ("n_prop", C.c_int32), ("max_iter", C.c_int32),
                 ("max_samples", C.c_int32), ("bound_update_interval", C.c_int32), ("flags", C.c_int32),
-                ("tol", C.c_double), ("efr", C.c_double), ("seed", C.c_uint64)]
+                ("tol", C.c_double), ("efr", C.c_double), ("seed", C.c_uint64),
+                ("n_prop_max", C.c_int32), ("target_batch", C.c_int32)]
 
 
 _lib = None

@@ -43,7 +43,10 @@ struct nf_sampler {
     int device, ncomp, flags, ndim;
     nf_ns_config cfg;
     int64_t n_run;
-    int K;
+    int K;                             // proposals per run per lock-step while the block is full (cfg.n_prop)
+    int Kmax;                          // ... and the most a run may get once few runs remain (cfg.n_prop_max)
+    int64_t cand_cap;                  // capacity of the candidate buffers (vectors)
+    int32_t *krun, *cand_off;          // [n_run] proposals of run r this cohort; [n_run] first candidate of active slot a
     // device state
     int32_t *pix_ids, *nlive;          // [n_run]
     double *live_u, *live_th, *live_l; // [n_run][nlive_max][ndim], .., [n_run][nlive_max]
@@ -62,7 +65,7 @@ struct nf_sampler {
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
     int walks;
-    int32_t *n_act_host;               // pinned
+    int32_t *n_act_host;               // pinned: {n_act, n_cand}
     cudaStream_t stream;
     int lock_iters;
     int64_t launches;
@@ -277,7 +280,8 @@ struct NsDev {
     // constrained random-walk state
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
-    int K, d, nlive_max, max_samples, max_iter, walks, flags;
+    const int32_t *krun, *cand_off;
+    int K, Kmax, d, nlive_max, max_samples, max_iter, walks, flags;
     double tol, efr;
     uint64_t seed;
     int lock;
@@ -300,10 +304,10 @@ __device__ void unit_ball(Philox &rng, int d, double *y)
 // ---- proposals: K candidates (or K random-walk steps) per active run ---------
 __global__ void ns_propose_kernel(const NsDev D)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
-    if (idx >= D.n_act * D.K) return;
-    const int a = idx / D.K, k = idx - a * D.K;
+    const int a = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
     const int r = D.act[a];
+    if (k >= D.krun[r]) return;
+    const int64_t idx = (int64_t)D.cand_off[a] + k;
     const int d = D.d;
     const double *B = D.bound + (int64_t)r * (d + d * d + 2);
     Philox rng(D.seed, (uint32_t)r, (uint32_t)D.lock, (uint32_t)k);
@@ -329,17 +333,17 @@ __global__ void ns_propose_kernel(const NsDev D)
     } else {
         // constrained random walk: chain k takes one step of size `scale` in the metric of the
         // live set's bounding ellipsoid; a cohort of K chains starts from random live points
-        double *cu = D.chain_u + ((int64_t)r * D.K + k) * d;
+        double *cu = D.chain_u + ((int64_t)r * D.Kmax + k) * d;
         if (D.coh_step[r] == 0) {
             const int nl = D.nlive[r];
             int j = (int)(rng.uniform() * (double)nl);
             j = min(j, nl - 1);
             const double *lu = D.live_u + ((int64_t)r * D.nlive_max + j) * d;
             const double *lt = D.live_th + ((int64_t)r * D.nlive_max + j) * d;
-            double *ct = D.chain_th + ((int64_t)r * D.K + k) * d;
+            double *ct = D.chain_th + ((int64_t)r * D.Kmax + k) * d;
             for (int i = 0; i < d; ++i) { cu[i] = lu[i]; ct[i] = lt[i]; }
-            D.chain_l[(int64_t)r * D.K + k] = D.live_l[(int64_t)r * D.nlive_max + j];
-            D.chain_moved[(int64_t)r * D.K + k] = 0;
+            D.chain_l[(int64_t)r * D.Kmax + k] = D.live_l[(int64_t)r * D.nlive_max + j];
+            D.chain_moved[(int64_t)r * D.Kmax + k] = 0;
         }
         unit_ball(rng, d, y);
         const double sc = D.scale[r];
@@ -352,7 +356,7 @@ __global__ void ns_propose_kernel(const NsDev D)
             if (!(v > 0.0 && v < 1.0)) ok = false;
         }
     }
-    double *ou = D.cand_u + (int64_t)idx * d, *ot = D.cand_th + (int64_t)idx * d;
+    double *ou = D.cand_u + idx * d, *ot = D.cand_th + idx * d;
     for (int j = 0; j < d; ++j) {
         const double v = ok ? u[j] : nan("");    // NaN -> NaN lnL -> never accepted
         ou[j] = v;
@@ -434,13 +438,13 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= D.n_act) return;
     const int r = D.act[w];
-    const int nl = D.nlive[r], d = D.d, K = D.K;
+    const int nl = D.nlive[r], d = D.d, K = D.krun[r], KS = D.Kmax;
     RunState S;
     S.lnZ = D.lnZ[r]; S.H = D.H[r]; S.lmax = D.lmax[r]; S.it = D.it[r]; S.nd = D.n_dead[r]; S.done = false;
     int64_t nev = D.n_eval[r];
     // ln(1 - exp(-1/nlive)): ln of the prior-mass shell X_{i-1} - X_i relative to X_{i-1}
     const double lnshell = log(-expm1(-1.0 / (double)nl));
-    const int64_t c0 = (int64_t)w * K;          // candidate slots of this run in this iteration
+    const int64_t c0 = (int64_t)D.cand_off[w];  // candidate slots of this run in this iteration
     int mode = D.mode[r];
     if (mode == 0) {
         int n_ok = 0, n_acc = 0;
@@ -476,11 +480,11 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
             const bool ok = cu[0] == cu[0];
             if (ok) ++nok;
             if (ok && lc > lstar) {
-                double *hu = D.chain_u + ((int64_t)r * K + k) * d, *ht = D.chain_th + ((int64_t)r * K + k) * d;
+                double *hu = D.chain_u + ((int64_t)r * KS + k) * d, *ht = D.chain_th + ((int64_t)r * KS + k) * d;
                 const double *ct = D.cand_th + (c0 + k) * d;
                 for (int j = 0; j < d; ++j) { hu[j] = cu[j]; ht[j] = ct[j]; }
-                D.chain_l[(int64_t)r * K + k] = lc;
-                D.chain_moved[(int64_t)r * K + k] = 1;
+                D.chain_l[(int64_t)r * KS + k] = lc;
+                D.chain_moved[(int64_t)r * KS + k] = 1;
                 ++acc;
             }
         }
@@ -496,9 +500,9 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
         if (step >= D.walks) {
             // the cohort's end points are candidates for the then-current threshold, in order
             for (int k = 0; k < K && !S.done; ++k) {
-                if (!D.chain_moved[(int64_t)r * K + k]) continue;      // never moved: still a live point
-                try_insert(D, r, nl, lane, lnshell, D.chain_u + ((int64_t)r * K + k) * d,
-                           D.chain_th + ((int64_t)r * K + k) * d, D.chain_l[(int64_t)r * K + k], S);
+                if (!D.chain_moved[(int64_t)r * KS + k]) continue;      // never moved: still a live point
+                try_insert(D, r, nl, lane, lnshell, D.chain_u + ((int64_t)r * KS + k) * d,
+                           D.chain_th + ((int64_t)r * KS + k) * d, D.chain_l[(int64_t)r * KS + k], S);
             }
             // step size follows the acceptance fraction (target 1/2)
             const double facc = (double)cacc / (double)(K * D.walks);
@@ -515,9 +519,15 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     }
 }
 
-// ---- active-list compaction (single CTA) -------------------------------------
+// ---- active-list compaction + proposal plan of the next lock-step (single CTA) -------
+// Runs that finished leave the active list.  While the block is full every run proposes K
+// candidates per lock-step; once few runs remain each gets more (a multiple of K up to Kmax,
+// aiming at `target` vectors per launch) so that the tail of a wave still fills the GPU.  A
+// random-walk cohort keeps the size it started with.
 __global__ void __launch_bounds__(1024)
-ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t *n_act_host, int64_t n_run)
+ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t *n_act_host, int64_t n_run,
+                  const int32_t *mode, const int32_t *coh_step, int32_t *krun, int32_t *cand_off, int K, int Kmax,
+                  int64_t target)
 {
     __shared__ int s_cnt[1024];
     __shared__ int s_base;
@@ -540,7 +550,40 @@ ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t
         if (tid == 1023) s_base += s_cnt[1023];
         __syncthreads();
     }
-    if (tid == 0) { *n_act_dev = s_base; *n_act_host = s_base; }
+    const int n_act = s_base;
+    __syncthreads();
+    int knew = K;
+    if (n_act > 0 && Kmax > K) {
+        const int64_t want = (target + n_act - 1) / n_act;
+        int64_t m = (want + K - 1) / K;
+        if (m < 1) m = 1;
+        if (m * K > Kmax) m = Kmax / K;
+        knew = (int)m * K;
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n_act; base += 1024) {
+        const int a = base + tid;
+        int k = 0;
+        if (a < n_act) {
+            const int r = act[a];
+            if (mode[r] == 0 || coh_step[r] == 0) krun[r] = knew;
+            k = krun[r];
+        }
+        s_cnt[tid] = k;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = tid >= o ? s_cnt[tid - o] : 0;
+            __syncthreads();
+            s_cnt[tid] += v;
+            __syncthreads();
+        }
+        if (a < n_act) cand_off[a] = s_base + s_cnt[tid] - k;
+        __syncthreads();
+        if (tid == 1023) s_base += s_cnt[1023];
+        __syncthreads();
+    }
+    if (tid == 0) { *n_act_dev = n_act; n_act_host[0] = n_act; n_act_host[1] = s_base; }
 }
 
 // ---- finalisation: add the live points, normalise, pick best-fit / MAP ------
@@ -659,14 +702,18 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     std::memset(s, 0, sizeof(*s));
     s->px = px; s->pr = pr; s->device = px->device; s->ncomp = ncomp; s->flags = model_flags; s->ndim = ndim;
     s->cfg = *cfg; s->n_run = n_run; s->K = cfg->n_prop;
-    const size_t R = (size_t)n_run, NL = (size_t)cfg->nlive_max, D = (size_t)ndim, K = (size_t)s->K,
-                 MS = (size_t)cfg->max_samples;
+    s->Kmax = cfg->n_prop_max > cfg->n_prop ? (cfg->n_prop_max / cfg->n_prop) * cfg->n_prop : cfg->n_prop;
+    if (s->cfg.target_batch < 1) s->cfg.target_batch = 65536;
+    // sum_a k_a <= max(n_act K, target + n_act K) over a shrinking active list
+    s->cand_cap = n_run * (int64_t)s->K + (s->Kmax > s->K ? (int64_t)s->cfg.target_batch : 0);
+    const size_t R = (size_t)n_run, NL = (size_t)cfg->nlive_max, D = (size_t)ndim, K = (size_t)s->Kmax,
+                 MS = (size_t)cfg->max_samples, CC = (size_t)s->cand_cap;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     A(dalloc(&s->pix_ids, R)); A(dalloc(&s->nlive, R));
     A(dalloc(&s->live_u, R * NL * D)); A(dalloc(&s->live_th, R * NL * D)); A(dalloc(&s->live_l, R * NL));
-    A(dalloc(&s->cand_u, R * K * D)); A(dalloc(&s->cand_th, R * K * D)); A(dalloc(&s->cand_l, R * K));
-    A(dalloc(&s->cand_pix, R * K));
+    A(dalloc(&s->cand_u, CC * D)); A(dalloc(&s->cand_th, CC * D)); A(dalloc(&s->cand_l, CC));
+    A(dalloc(&s->cand_pix, CC)); A(dalloc(&s->krun, R)); A(dalloc(&s->cand_off, R));
     A(dalloc(&s->bound, R * (D + D * D + 2)));
     A(dalloc(&s->dead_th, R * MS * D)); A(dalloc(&s->dead_l, R * MS)); A(dalloc(&s->dead_lw, R * MS));
     A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
@@ -677,7 +724,7 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->eff_prop, R)); A(dalloc(&s->chain_moved, R * K)); A(dalloc(&s->lstar, R)); A(dalloc(&s->scale, R));
     A(dalloc(&s->chain_u, R * K * D)); A(dalloc(&s->chain_th, R * K * D)); A(dalloc(&s->chain_l, R * K));
     s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + ndim;
-    A(cudaMallocHost((void **)&s->n_act_host, sizeof(int32_t)));
+    A(cudaMallocHost((void **)&s->n_act_host, 2 * sizeof(int32_t)));
     A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(s->nlive, nlive, R * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -694,7 +741,7 @@ int nf_ns_free(nf_sampler *s)
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     void *ptrs[] = {s->pix_ids, s->nlive, s->live_u, s->live_th, s->live_l, s->cand_u, s->cand_th, s->cand_l,
-                    s->cand_pix, s->bound, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->lmax, s->lnZ_err,
+                    s->cand_pix, s->krun, s->cand_off, s->bound, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->lmax, s->lnZ_err,
                     s->n_dead, s->it, s->done, s->n_eval, s->bestfit, s->mapfit, s->act, s->n_act_dev,
                     s->mode, s->coh_step, s->coh_acc, s->eff_acc, s->eff_prop, s->chain_moved, s->lstar, s->scale,
                     s->chain_u, s->chain_th, s->chain_l};
@@ -743,7 +790,15 @@ int nf_ns_run(nf_sampler *s)
             s->launches += 2;
         }
     }
-    int n_act = (int)R;
+    // the first proposal plan
+    if (rc == NF_OK) {
+        ns_compact_kernel<<<1, 1024, 0, st>>>(s->done, s->act, s->n_act_dev, s->n_act_host, R, s->mode, s->coh_step,
+                                              s->krun, s->cand_off, K, s->Kmax, (int64_t)s->cfg.target_batch);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = (int)e;
+    }
+    int n_act = rc == NF_OK ? s->n_act_host[0] : 0;
+    int64_t n_cand = rc == NF_OK ? s->n_act_host[1] : 0;
     int lock = 0;
     // lock-step iterations are bounded: a run needs at most max_iter * walks of them
     const int64_t lock_cap = (int64_t)s->cfg.max_iter * (int64_t)(s->walks + 1);
@@ -757,21 +812,24 @@ int nf_ns_run(nf_sampler *s)
         D.n_eval = s->n_eval; D.mode = s->mode; D.coh_step = s->coh_step; D.coh_acc = s->coh_acc;
         D.eff_acc = s->eff_acc; D.eff_prop = s->eff_prop; D.chain_moved = s->chain_moved; D.lstar = s->lstar;
         D.scale = s->scale; D.chain_u = s->chain_u; D.chain_th = s->chain_th; D.chain_l = s->chain_l;
-        D.K = K; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
+        D.krun = s->krun; D.cand_off = s->cand_off;
+        D.K = K; D.Kmax = s->Kmax; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
         D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
         D.lock = lock;
         ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->nlive, s->it, s->live_u, s->bound, NL, d, s->cfg.efr,
                                                 s->mode, s->coh_step);
-        const int nc = n_act * K;
-        ns_propose_kernel<<<(nc + 127) / 128, 128, 0, st>>>(D);
-        rc = score(s, s->cand_th, s->cand_pix, K, nc, s->cand_l);
+        if (n_cand > s->cand_cap) { rc = NF_EINVAL; break; }     // cannot happen (see cand_cap)
+        ns_propose_kernel<<<dim3((unsigned)((s->Kmax + 127) / 128), (unsigned)n_act), 128, 0, st>>>(D);
+        rc = score(s, s->cand_th, s->cand_pix, K, n_cand, s->cand_l);
         if (rc != NF_OK) break;
         ns_update_kernel<<<(n_act * 32 + 127) / 128, 128, 0, st>>>(D);
-        ns_compact_kernel<<<1, 1024, 0, st>>>(s->done, s->act, s->n_act_dev, s->n_act_host, R);
+        ns_compact_kernel<<<1, 1024, 0, st>>>(s->done, s->act, s->n_act_dev, s->n_act_host, R, s->mode, s->coh_step,
+                                              s->krun, s->cand_off, K, s->Kmax, (int64_t)s->cfg.target_batch);
         s->launches += 4;
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = (int)e; break; }
-        n_act = *s->n_act_host;
+        n_act = s->n_act_host[0];
+        n_cand = s->n_act_host[1];
         ++lock;
         if (getenv("NF_NS_DEBUG") && (lock % atoi(getenv("NF_NS_DEBUG"))) == 0 && n_act > 0) {
             // diagnostics of the first still-active run

@@ -10,6 +10,7 @@ pixels enter the next wave.  Multi-GPU = disjoint contiguous pixel blocks, one
 process per GPU, one store chunk per process, no collective.
 """
 import os
+import threading
 import time
 from collections.abc import Iterable
 
@@ -206,10 +207,12 @@ class CubeFitter:
     }
 
     def __init__(self, stack, utrans, runner_cls, runner_kwargs=None, lnZ_thresh=11, ncomp_max=2, mn_kwargs=None,
-                 nlive_snr_fact=5, n_prop=32, max_pixels_per_wave=16384, seed=1234, store_posteriors=True):
+                 nlive_snr_fact=5, n_prop=32, max_pixels_per_wave=16384, seed=1234, store_posteriors=True,
+                 n_streams=4, min_pixels_per_stream=256):
         """Same arguments as the reference (main.py:388-421) plus the batching knobs
         `n_prop` (proposals per pixel per lock-step iteration), `max_pixels_per_wave`
-        (pixels in flight per device wave) and `seed`."""
+        (pixels in flight per device wave), `n_streams` (sub-blocks of a wave that escalate
+        concurrently, each at least `min_pixels_per_stream` pixels) and `seed`."""
         self.stack = stack
         self.utrans = utrans
         self.runner_cls = runner_cls
@@ -222,6 +225,8 @@ class CubeFitter:
         self.nlive_snr_fact = nlive_snr_fact
         self.n_prop = n_prop
         self.max_pixels_per_wave = max_pixels_per_wave
+        self.n_streams = n_streams
+        self.min_pixels_per_stream = min_pixels_per_stream
         self.seed = seed
         self.store_posteriors = store_posteriors
         self.stats = {}
@@ -265,42 +270,72 @@ class CubeFitter:
             n_chan_tot = blk.n_spec * blk.n_chan
             old_lnZ = null.copy()
             nbest = np.zeros(vidx.size, dtype=np.int32)
-            active = np.arange(vidx.size)
             out['lnZ'][w0 + vidx, 0] = null
-            for ncomp in range(1, self.ncomp_max + 1):
-                if active.size == 0:
-                    break
-                if verbose:
-                    print(f'-- wave {w0}: N = {ncomp}: {active.size} pixels')
-                kw = {k: v for k, v in self.runner_kwargs.items() if k in ('cold', 'lte')}
-                ns = NestedSamplingBatch(blk, self.utrans, ncomp, pix_ids=active, nlive=nlive[active],
-                                         tol=self.mn_kwargs['tol'], efr=self.mn_kwargs['efr'], n_prop=self.n_prop,
-                                         seed=self.seed + 7919 * ncomp + w0,
-                                         max_iter=self.mn_kwargs.get('maxiter', 1_000_000), **kw)
-                res = ns.run()
-                n_evals += int(res['n_evals'].sum())
-                assert np.isfinite(res['lnZ']).all()           # main.py:463
-                gi = w0 + vidx[active]
-                out['lnZ'][gi, ncomp] = res['lnZ']
-                out['lnZ_err'][gi, ncomp] = res['lnZ_err']
-                out['max_loglike'][gi, ncomp] = res['max_loglike']
-                out['n_samples'][gi, ncomp] = res['n_samples']
-                if group_root is not None:
-                    for r, a in enumerate(active):
-                        g = group_root.require_group(f'/pix/{lon[vidx[a]]}/{lat[vidx[a]]}')
-                        sub = g.create_group(f'{ncomp}')
-                        attrs, dsets = ns.products(r, null[a], n_chan_tot)
-                        for k, v in attrs.items():
-                            sub.attrs[k] = v
-                        for k, v in dsets.items():
-                            if k == 'posteriors' and not self.store_posteriors:
-                                continue
-                            sub.create_dataset(k, data=v)
-                ns.close()
-                improved = res['lnZ'] - old_lnZ[active] >= self.lnZ_thresh     # main.py:464-469
-                old_lnZ[active[improved]] = res['lnZ'][improved]
-                nbest[active[improved]] = ncomp
-                active = active[improved]
+            evals = []
+            lock = threading.Lock()
+
+            def fit_sub(active, tag):
+                """ncomp escalation (main.py:450-469) of one sub-block of the wave's pixels."""
+                for ncomp in range(1, self.ncomp_max + 1):
+                    if active.size == 0:
+                        break
+                    if verbose:
+                        print(f'-- wave {w0}.{tag}: N = {ncomp}: {active.size} pixels')
+                    kw = {k: v for k, v in self.runner_kwargs.items() if k in ('cold', 'lte')}
+                    ns = NestedSamplingBatch(blk, self.utrans, ncomp, pix_ids=active, nlive=nlive[active],
+                                             tol=self.mn_kwargs['tol'], efr=self.mn_kwargs['efr'], n_prop=self.n_prop,
+                                             seed=self.seed + 7919 * ncomp + w0 + 104729 * tag,
+                                             max_iter=self.mn_kwargs.get('maxiter', 1_000_000), **kw)
+                    res = ns.run()
+                    evals.append(int(res['n_evals'].sum()))
+                    assert np.isfinite(res['lnZ']).all()           # main.py:463
+                    gi = w0 + vidx[active]
+                    out['lnZ'][gi, ncomp] = res['lnZ']
+                    out['lnZ_err'][gi, ncomp] = res['lnZ_err']
+                    out['max_loglike'][gi, ncomp] = res['max_loglike']
+                    out['n_samples'][gi, ncomp] = res['n_samples']
+                    if group_root is not None:
+                        with lock:
+                            for r, a in enumerate(active):
+                                g = group_root.require_group(f'/pix/{lon[vidx[a]]}/{lat[vidx[a]]}')
+                                sub = g.create_group(f'{ncomp}')
+                                attrs, dsets = ns.products(r, null[a], n_chan_tot)
+                                for k, v in attrs.items():
+                                    sub.attrs[k] = v
+                                for k, v in dsets.items():
+                                    if k == 'posteriors' and not self.store_posteriors:
+                                        continue
+                                    sub.create_dataset(k, data=v)
+                    ns.close()
+                    improved = res['lnZ'] - old_lnZ[active] >= self.lnZ_thresh     # main.py:464-469
+                    old_lnZ[active[improved]] = res['lnZ'][improved]
+                    nbest[active[improved]] = ncomp
+                    active = active[improved]
+
+            # Sub-blocks of the wave escalate independently on their own streams (one host thread
+            # each; the sampler call releases the GIL), so that the thin tail of one sub-block's
+            # run overlaps the bulk of another's instead of idling the GPU.
+            n_sub = max(1, min(self.n_streams, vidx.size // max(1, self.min_pixels_per_stream)))
+            subs = np.array_split(np.arange(vidx.size), n_sub)
+            if n_sub == 1:
+                fit_sub(subs[0], 0)
+            else:
+                errors = []
+
+                def guarded(sub, tag):
+                    try:
+                        fit_sub(sub, tag)
+                    except BaseException as exc:   # re-raised in the caller's thread
+                        errors.append(exc)
+
+                threads = [threading.Thread(target=guarded, args=(sub, t)) for t, sub in enumerate(subs)]
+                for th in threads:
+                    th.start()
+                for th in threads:
+                    th.join()
+                if errors:
+                    raise errors[0]
+            n_evals += sum(evals)
             out['nbest'][w0 + vidx] = nbest
             if group_root is not None:
                 for a in range(vidx.size):

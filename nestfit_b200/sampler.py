@@ -36,10 +36,13 @@ class NestedSamplingBatch:
     """Lock-step nested sampling of ``n_run`` (pixel, ncomp) fits on one GPU."""
 
     def __init__(self, block, utrans, ncomp, pix_ids=None, nlive=100, tol=1.0, efr=0.3, n_prop=32, seed=1,
-                 max_iter=1_000_000, max_samples=None, cold=False, lte=False, method='auto', walks=0):
+                 max_iter=1_000_000, max_samples=None, cold=False, lte=False, method='auto', walks=0,
+                 n_prop_max=None, target_batch=65536):
         """method: 'auto' = ellipsoidal rejection sampling that hands a run over to a
         constrained random walk once its acceptance stalls; 'ellipsoid' / 'rwalk' force one.
-        walks: random-walk steps per new point (0 = 20 + ndim)."""
+        walks: random-walk steps per new point (0 = 20 + ndim).
+        n_prop_max / target_batch: once few runs are still active each gets up to n_prop_max
+        proposals per lock-step (default 4 n_prop) so that a launch keeps ~target_batch vectors."""
         lib = _lib.load()
         self.block, self.utrans, self.ncomp = block, utrans, int(ncomp)
         if pix_ids is None:
@@ -56,7 +59,9 @@ class NestedSamplingBatch:
         self.cfg = NsConfig(nlive_max=nlive_max, n_prop=int(n_prop), max_iter=int(min(max_iter, 2**31 - 1)),
                             max_samples=int(max_samples), bound_update_interval=int(walks),
                             flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method], tol=float(tol),
-                            efr=float(efr), seed=int(seed))
+                            efr=float(efr), seed=int(seed),
+                            n_prop_max=int(4 * n_prop if n_prop_max is None else n_prop_max),
+                            target_batch=int(target_batch))
         flags = (_lib.NF_FLAG_COLD if cold else 0) | (_lib.NF_FLAG_LTE if lte else 0)
         out = C.c_void_p()
         _lib.check(lib.nf_ns_create(block.handle, utrans.handle(block.device), self.ncomp, flags,

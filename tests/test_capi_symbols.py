@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(nb):
 def test_abi_version_and_error_strings(nb):
     from nestfit_b200 import _lib
     lib = _lib.load()
-    assert lib.nf_abi_version() == 1
+    assert lib.nf_abi_version() == 2
     assert lib.nf_error_string(0) == b"ok"
     assert lib.nf_error_string(-1) == b"invalid argument"
 
