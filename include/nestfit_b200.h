@@ -15,6 +15,8 @@
  *       -> nf_nh3_predict
  *   - `gauss_predict` / `GaussianRunner.c_loglikelihood`     nestfit/models/gaussian.pyx:53-54,98-102
  *       -> nf_gauss_predict / nf_gauss_loglike
+ *   - `nnhp_predict` / `DiazenyliumRunner.c_loglikelihood`   nestfit/models/diazenylium.pyx:140-158,206-215
+ *       -> nf_n2hp_predict / nf_n2hp_loglike
  *   - `AmmoniaSpectrum.__init__`, `Spectrum.__init__`        nestfit/models/ammonia.pyx:245-277, nestfit/core/core.pyx:488-520
  *       -> nf_pixels_create (+ nf_pixels_null_lnz)
  *   - `PriorTransformer.c_transform`                         nestfit/core/core.pyx:459-476
@@ -25,7 +27,8 @@
  *
  * Layouts: parameter vectors are parameter-major / component-minor,
  * `[p0c0,p0c1,..,p1c0,..]` (ammonia.pyx:337-343); NH3 order voff,trot,tex,ntot,
- * sigm,orth; Gaussian order voff,sigm,peak (gaussian.pyx:27-30).
+ * sigm,orth; Gaussian order voff,sigm,peak (gaussian.pyx:27-30); N2H+ order
+ * voff,tex,ltau,sigm (diazenylium.pyx:148-153).
  */
 #ifndef NESTFIT_B200_H
 #define NESTFIT_B200_H
@@ -46,7 +49,7 @@ enum {
     NF_ENODEV = -3    /* no usable CUDA device                                */
 };
 
-enum { NF_MODEL_NH3 = 1, NF_MODEL_GAUSS = 2 };
+enum { NF_MODEL_NH3 = 1, NF_MODEL_GAUSS = 2, NF_MODEL_N2HP = 3 };
 enum { NF_F32 = 0, NF_F64 = 1 };
 /* flags of the NH3 model (ammonia.pyx:344-347) */
 enum { NF_FLAG_COLD = 1, NF_FLAG_LTE = 2 };
@@ -74,6 +77,8 @@ int nf_device_count(int *count);
  * transition (ammonia.pyx:245-271), `rest_freq` ignored.
  * model == NF_MODEL_GAUSS: n_spec must be 1 and `rest_freq[0]` is the line rest
  * frequency in Hz (gaussian.pyx:31-32).
+ * model == NF_MODEL_N2HP: `trans_id[s]` in 1..3 selects J = 1-0, 2-1, 3-2
+ * (diazenylium.pyx:105-138), `rest_freq` ignored.
  * Data are stored as FP32 in HBM, channel-contiguous, rows padded to 32.
  */
 int nf_pixels_create(int device, int model, int64_t n_pix, int n_spec, int n_chan,
@@ -113,6 +118,12 @@ int nf_nh3_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
 int nf_gauss_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,
                      const int32_t *pix_of_vec_dev, int64_t vecs_per_pix, int64_t B,
                      int ncomp, double *lnL_dev, void *stream);
+/* N2H+: params [B][4*ncomp] = voff, tex, log10(tau_main), sigm (diazenylium.pyx:140-154) */
+int nf_n2hp_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,
+                    const int32_t *pix_of_vec_dev, int64_t vecs_per_pix, int64_t B,
+                    int ncomp, double *lnL_dev, void *stream);
+int nf_n2hp_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
+                    int64_t B, int ncomp, float *pred_dev, void *stream);
 int nf_gauss_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
                      int64_t B, int ncomp, float *pred_dev, void *stream);
 
@@ -130,6 +141,11 @@ int nf_nh3_predict_host(const nf_pixels *px, const void *params_host, int param_
                         int64_t B, int ncomp, int flags, float *pred_host);
 int nf_gauss_predict_host(const nf_pixels *px, const void *params_host, int param_dtype,
                           int64_t B, int ncomp, float *pred_host);
+int nf_n2hp_loglike_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                         const int32_t *pix_of_vec_host, int64_t vecs_per_pix,
+                         int64_t B, int ncomp, double *lnL_host);
+int nf_n2hp_predict_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                         int64_t B, int ncomp, float *pred_host);
 
 /* ---- prior transform ---------------------------------------------------- */
 int nf_priors_create(int device, const nf_prior_desc *priors, int n_prior,

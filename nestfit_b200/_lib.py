@@ -13,7 +13,7 @@ import os as _os
 # NESTFIT_B200_LIB lets kernel experiments load an alternative build of the same ABI
 LIB_PATH = Path(_os.environ.get("NESTFIT_B200_LIB", _PKG / "libnestfit_b200.so"))
 
-NF_MODEL_NH3, NF_MODEL_GAUSS = 1, 2
+NF_MODEL_NH3, NF_MODEL_GAUSS, NF_MODEL_N2HP = 1, 2, 3
 NF_F32, NF_F64 = 0, 1
 NF_FLAG_COLD, NF_FLAG_LTE = 1, 2
 NF_MAX_SPEC = 6
@@ -61,6 +61,10 @@ _SIGNATURES = {
     "nf_nh3_predict": ([_VP, _VP, _I, _I64, _I, _I, _VP, _VP], _I),
     "nf_gauss_loglike": ([_VP, _VP, _I, _VP, _I64, _I64, _I, _VP, _VP], _I),
     "nf_gauss_predict": ([_VP, _VP, _I, _I64, _I, _VP, _VP], _I),
+    "nf_n2hp_loglike": ([_VP, _VP, _I, _VP, _I64, _I64, _I, _VP, _VP], _I),
+    "nf_n2hp_predict": ([_VP, _VP, _I, _I64, _I, _VP, _VP], _I),
+    "nf_n2hp_loglike_host": ([_VP, _VP, _I, _VP, _I64, _I64, _I, _VP], _I),
+    "nf_n2hp_predict_host": ([_VP, _VP, _I, _I64, _I, _VP], _I),
     "nf_nh3_loglike_host": ([_VP, _VP, _I, _VP, _I64, _I64, _I, _I, _VP], _I),
     "nf_gauss_loglike_host": ([_VP, _VP, _I, _VP, _I64, _I64, _I, _VP], _I),
     "nf_nh3_predict_host": ([_VP, _VP, _I, _I64, _I, _I, _VP], _I),

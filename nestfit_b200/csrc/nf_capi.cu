@@ -7,6 +7,7 @@
 
 #include "nf_internal.cuh"
 #include "../../include/nf_nh3_tables.h"
+#include "../../include/nf_n2hp_tables.h"
 
 thread_local double g_nf_last_kernel_ms = 0.0;
 thread_local int64_t g_nf_last_launches = 0;
@@ -16,6 +17,19 @@ namespace {
 const double kNu[NF_NH3_NTRANS] = NF_NH3_REST_FREQ_INIT;
 const double kEa[NF_NH3_NTRANS] = NF_NH3_EINSTEIN_A_INIT;
 const int kOff[NF_NH3_NTRANS + 1] = NF_NH3_LINE_OFFSET_INIT;
+const double kNuN2hp[NF_N2HP_NTRANS] = NF_N2HP_REST_FREQ_INIT;
+const int kOffN2hp[NF_N2HP_NTRANS + 1] = NF_N2HP_LINE_OFFSET_INIT;
+
+inline bool is_hyperfine(int model) { return model == NF_MODEL_NH3 || model == NF_MODEL_N2HP; }
+inline int model_nparams(int model) { return model == NF_MODEL_NH3 ? 6 : (model == NF_MODEL_N2HP ? 4 : 3); }
+inline cudaError_t launch_model(int model, const NfLikeArgs &a, cudaStream_t st)
+{
+    switch (model) {
+    case NF_MODEL_NH3: return nf_launch_nh3(a, st);
+    case NF_MODEL_N2HP: return nf_launch_n2hp(a, st);
+    default: return nf_launch_gauss(a, st);
+    }
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -60,6 +74,14 @@ int fill_meta(nf_pixels *px, const double *nu_min, const double *nu_chan, const 
             m.fracterm = NF_CCMS * NF_CCMS * kEa[t - 1] / (8.0 * M_PI * m.nu0 * m.nu0);
             m.width_c = NF_CKMS / (m.nu0 * std::sqrt(2.0 * M_PI));
             m.hnu_k = NF_H * m.nu0 / NF_KB;
+        } else if (px->model == NF_MODEL_N2HP) {
+            const int t = trans_id ? trans_id[s] : 0;
+            if (t < 1 || t > NF_N2HP_NTRANS) return NF_EINVAL;                  // diazenylium.pyx:128
+            m.J = t;
+            m.nu0 = kNuN2hp[t - 1];
+            m.line_off = NF_NH3_NLINES_TOTAL + kOffN2hp[t - 1];                 // flat line list of nf_nh3.cu
+            m.nlines = kOffN2hp[t] - kOffN2hp[t - 1];
+            m.hnu_k = NF_H * m.nu0 / NF_KB;
         } else {
             if (!rest_freq || !(rest_freq[s] > 0.0)) return NF_EINVAL;
             m.nu0 = rest_freq[s];
@@ -75,7 +97,7 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     if (!out) return NF_EINVAL;
     *out = nullptr;
     if (n_pix <= 0 || n_spec <= 0 || n_spec > NF_MAX_SPEC || n_chan < 2 || n_chan > 65535) return NF_EINVAL;
-    if (model != NF_MODEL_NH3 && model != NF_MODEL_GAUSS) return NF_EINVAL;
+    if (model != NF_MODEL_NH3 && model != NF_MODEL_GAUSS && model != NF_MODEL_N2HP) return NF_EINVAL;
     if (model == NF_MODEL_GAUSS && n_spec != 1) return NF_EINVAL;
     if (!nu_min || !nu_chan) return NF_EINVAL;
     nf_pixels *px = new (std::nothrow) nf_pixels();
@@ -144,9 +166,9 @@ int make_args(const nf_pixels *px, const void *params, int param_dtype, const in
 {
     if (!px || !params || B < 0 || ncomp < 1) return NF_EINVAL;
     if (param_dtype != NF_F32 && param_dtype != NF_F64) return NF_EINVAL;
-    if (px->model == NF_MODEL_NH3 && ncomp > NF_MAX_NCOMP_NH3) return NF_EINVAL;
+    if (is_hyperfine(px->model) && ncomp > NF_MAX_NCOMP_NH3) return NF_EINVAL;
     if (px->model == NF_MODEL_GAUSS && ncomp > NF_MAX_NCOMP_GAUSS) return NF_EINVAL;
-    if (px->model == NF_MODEL_NH3 && ncomp * px->n_spec > 32) return NF_EINVAL;
+    if (is_hyperfine(px->model) && ncomp * px->n_spec > 32) return NF_EINVAL;
     if (use_data && !pix_of_vec && vecs_per_pix < 1) return NF_EINVAL;
     std::memset(a, 0, sizeof(*a));
     a->data = use_data ? px->data : nullptr;
@@ -177,8 +199,7 @@ int run_device(const nf_pixels *px, const NfLikeArgs &a, void *stream)
     DeviceGuard g(px->device);
     if (!g.ok) return NF_ENODEV;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = px->model == NF_MODEL_NH3 ? nf_launch_nh3(a, st) : nf_launch_gauss(a, st);
-    return (int)e;
+    return (int)launch_model(px->model, a, st);
 }
 
 // Host-buffer call: chunks of vectors ping-pong over two streams so the H2D
@@ -192,7 +213,7 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
     if (!params_host || (!lnL_host && !pred_host)) return NF_EINVAL;
     DeviceGuard g(px->device);
     if (!g.ok) return NF_ENODEV;
-    const int n_model = model == NF_MODEL_NH3 ? 6 : 3;
+    const int n_model = model_nparams(model);
     const int ndim = n_model * ncomp;
     const size_t psz = param_dtype == NF_F64 ? 8 : 4;
     const bool want_pred = pred_host != nullptr;
@@ -249,7 +270,7 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
             a.inv2s2 = px->inv2s2 + (b0 / a.vecs_per_pix) * px->n_spec;
         }
         NF_CUDA(cudaEventRecord(ev0[slot], st));
-        cudaError_t e = model == NF_MODEL_NH3 ? nf_launch_nh3(a, st) : nf_launch_gauss(a, st);
+        cudaError_t e = launch_model(model, a, st);
         if (e != cudaSuccess) { status = (int)e; break; }
         NF_CUDA(cudaEventRecord(ev1[slot], st));
         ++launches;
@@ -416,6 +437,44 @@ int nf_nh3_predict(const nf_pixels *px, const void *params_dev, int param_dtype,
     int rc = make_args(px, params_dev, param_dtype, nullptr, 1, B, ncomp, flags, nullptr, pred_dev, false, &a);
     if (rc != NF_OK) return rc;
     return run_device(px, a, stream);
+}
+
+int nf_n2hp_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,
+                    const int32_t *pix_of_vec_dev, int64_t vecs_per_pix, int64_t B, int ncomp, double *lnL_dev,
+                    void *stream)
+{
+    if (!px || px->model != NF_MODEL_N2HP || !lnL_dev) return NF_EINVAL;
+    NfLikeArgs a;
+    int rc = make_args(px, params_dev, param_dtype, pix_of_vec_dev, vecs_per_pix, B, ncomp, 0, lnL_dev,
+                       nullptr, true, &a);
+    if (rc != NF_OK) return rc;
+    return run_device(px, a, stream);
+}
+
+int nf_n2hp_predict(const nf_pixels *px, const void *params_dev, int param_dtype, int64_t B, int ncomp,
+                    float *pred_dev, void *stream)
+{
+    if (!px || px->model != NF_MODEL_N2HP || !pred_dev) return NF_EINVAL;
+    NfLikeArgs a;
+    int rc = make_args(px, params_dev, param_dtype, nullptr, 1, B, ncomp, 0, nullptr, pred_dev, false, &a);
+    if (rc != NF_OK) return rc;
+    return run_device(px, a, stream);
+}
+
+int nf_n2hp_loglike_host(const nf_pixels *px, const void *params_host, int param_dtype,
+                         const int32_t *pix_of_vec_host, int64_t vecs_per_pix, int64_t B, int ncomp,
+                         double *lnL_host)
+{
+    if (!lnL_host) return NF_EINVAL;
+    return run_host(px, NF_MODEL_N2HP, params_host, param_dtype, pix_of_vec_host, vecs_per_pix, B, ncomp, 0,
+                    lnL_host, nullptr);
+}
+
+int nf_n2hp_predict_host(const nf_pixels *px, const void *params_host, int param_dtype, int64_t B, int ncomp,
+                         float *pred_host)
+{
+    if (!pred_host) return NF_EINVAL;
+    return run_host(px, NF_MODEL_N2HP, params_host, param_dtype, nullptr, 1, B, ncomp, 0, nullptr, pred_host);
 }
 
 int nf_gauss_loglike(const nf_pixels *px, const void *params_dev, int param_dtype,

@@ -85,12 +85,14 @@ struct NfLikeArgs {
     int cold, lte;
     int need_para, need_ortho;
     int tile_vecs;              // parameter vectors per CTA tile (0 -> NF_TILE_VECS)
-    int npair;                  // NH3 kernel: pair records per parity (set by the launcher)
+    int npair;                  // hyperfine kernel: pair records per parity (set by the launcher)
+    int nkey;                   // hyperfine kernel: line keys per component (set by the launcher)
     NfSpecMeta spec[NF_MAX_SPEC];
 };
 
 // launchers (nf_model.cu)
 cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st);          // nf_nh3.cu
+cudaError_t nf_launch_n2hp(const NfLikeArgs &a, cudaStream_t st);         // nf_nh3.cu (N2H+ front end)
 cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st);   // nf_model.cu (previous kernel, NF_NH3_LEGACY=1)
 cudaError_t nf_launch_gauss(const NfLikeArgs &a, cudaStream_t st);
 cudaError_t nf_model_init_device_tables(int device);

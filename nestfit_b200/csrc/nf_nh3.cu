@@ -30,13 +30,16 @@
 #include "nf_internal.cuh"
 #include "nf_device.cuh"
 #include "../../include/nf_nh3_tables.h"
+#include "../../include/nf_n2hp_tables.h"
 
 #define NH3_WARPS NF_WARPS_PER_CTA
 #define NH3_KEY_NEVER 30000     // chunk key of a line above the band
 
 // ---- device tables ---------------------------------------------------------
-__device__ double n_line_freq[NF_NH3_NLINES_TOTAL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
-__device__ float n_line_l2w[NF_NH3_NLINES_TOTAL];    // log2 of the tau weights  ammonia.pyx:168-228
+// NH3 lines first, then the N2H+ lines (NfSpecMeta::line_off indexes this flat list)
+#define NH3_NLINES_ALL (NF_NH3_NLINES_TOTAL + NF_N2HP_NLINES_TOTAL)
+__device__ double n_line_freq[NH3_NLINES_ALL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
+__device__ float n_line_l2w[NH3_NLINES_ALL];    // log2 of the tau weights  ammonia.pyx:168-228, diazenylium.pyx:66-92
 __device__ double n_iem_y[NF_IEM_SIZE];              // 1/(exp(x_k)-1)         hyperfine.pyx:19
 __constant__ double n_iem_xmin, n_iem_xmax, n_iem_step, n_iem_inv_dx;
 
@@ -44,6 +47,10 @@ static const double hn_nu[NF_NH3_NTRANS] = NF_NH3_REST_FREQ_INIT;
 static const int hn_off[NF_NH3_NTRANS + 1] = NF_NH3_LINE_OFFSET_INIT;
 static const double hn_voff[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_VOFF_INIT;
 static const double hn_wt[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_WEIGHT_INIT;
+static const double hd_nu[NF_N2HP_NTRANS] = NF_N2HP_REST_FREQ_INIT;
+static const int hd_off[NF_N2HP_NTRANS + 1] = NF_N2HP_LINE_OFFSET_INIT;
+static const double hd_voff[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_VOFF_INIT;
+static const double hd_wt[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_WEIGHT_INIT;
 
 static cudaError_t nh3_init_device_tables()
 {
@@ -52,12 +59,17 @@ static cudaError_t nh3_init_device_tables()
     if (e) return e;
     static bool done[64] = {false};
     if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
-    double freq[NF_NH3_NLINES_TOTAL];
-    float l2w[NF_NH3_NLINES_TOTAL];
+    double freq[NH3_NLINES_ALL];
+    float l2w[NH3_NLINES_ALL];
     for (int t = 0; t < NF_NH3_NTRANS; ++t)
         for (int i = hn_off[t]; i < hn_off[t + 1]; ++i) {
             freq[i] = (1.0 - hn_voff[i] / NF_CKMS) * hn_nu[t];
             l2w[i] = (float)std::log2(hn_wt[i]);
+        }
+    for (int t = 0; t < NF_N2HP_NTRANS; ++t)
+        for (int i = hd_off[t]; i < hd_off[t + 1]; ++i) {
+            freq[NF_NH3_NLINES_TOTAL + i] = (1.0 - hd_voff[i] / NF_CKMS) * hd_nu[t];
+            l2w[NF_NH3_NLINES_TOTAL + i] = (float)std::log2(hd_wt[i]);     // -inf for a zero weight
         }
     if ((e = cudaMemcpyToSymbol(n_line_freq, freq, sizeof(freq)))) return e;
     if ((e = cudaMemcpyToSymbol(n_line_l2w, l2w, sizeof(l2w)))) return e;
@@ -102,8 +114,8 @@ struct __align__(16) Nh3Pair {
     float4 h;   // {h_0, h_1, -, -}                 window <=> |j - R'| <= h
 };
 
-// Per-warp scratch: the pair records (capacity set at launch from the transitions in use)
-// followed by this fixed part.
+// Per-warp scratch: the pair records and the line keys (capacities set at launch from the
+// transitions in use) followed by this fixed part.
 template <int NC>
 struct __align__(16) Nh3Scratch {
     uint4 tab[36];                        // per chunk and component: smem address of the first pair | pairs << 18;
@@ -111,7 +123,6 @@ struct __align__(16) Nh3Scratch {
     float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
     double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
     float tauL[32];                       // log2(log2(e) * tau_main)
-    short2 key[NC][32];                   // per line: first chunk, first chunk after its window
 };
 
 // (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels other than J = 1, 2)
@@ -119,7 +130,9 @@ struct __align__(16) Nh3Scratch {
 #define NH3_CK_F ((float)(NF_HK * (NF_CROT - NF_BROT)))
 
 // ---- S: batched set-up, lanes <-> (vector, component, spectrum) -----------------
-template <int NC, typename PT>
+// MODEL 0: NH3 (voff, trot, tex, ntot, sigm, orth; ammonia.pyx:326-361);
+// MODEL 1: N2H+ (voff, tex, ltau, sigm; diazenylium.pyx:140-154).
+template <int MODEL, int NC, typename PT>
 __device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC> &sc, int64_t bb, int nb,
                                              int lane)
 {
@@ -129,13 +142,20 @@ __device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC>
     const int r = lane - kk * ipv;
     const int c = r / n_spec, s = r - c * n_spec;
     const bool valid = kk < nb;
-    const int64_t pbase = (bb + (valid ? kk : 0)) * (6 * NC);
+    const int64_t pbase = (bb + (valid ? kk : 0)) * ((MODEL == 0 ? 6 : 4) * NC);
     const NfSpecMeta &sm = a.spec[s];
     const double voff = ld_param<PT>(a.params, pbase + 0 * NC + c);
+    double tex, sigm, tau_main;
+    if constexpr (MODEL == 1) {
+        tex = ld_param<PT>(a.params, pbase + 1 * NC + c);
+        const double ltau = ld_param<PT>(a.params, pbase + 2 * NC + c);
+        sigm = ld_param<PT>(a.params, pbase + 3 * NC + c);
+        tau_main = exp10(ltau);                                          // hyperfine.pyx:63
+    } else {
     double trot = ld_param<PT>(a.params, pbase + 1 * NC + c);
-    double tex = ld_param<PT>(a.params, pbase + 2 * NC + c);
+    tex = ld_param<PT>(a.params, pbase + 2 * NC + c);
     const double ntot = ld_param<PT>(a.params, pbase + 3 * NC + c);
-    const double sigm = ld_param<PT>(a.params, pbase + 4 * NC + c);
+    sigm = ld_param<PT>(a.params, pbase + 4 * NC + c);
     const double orth = ld_param<PT>(a.params, pbase + 5 * NC + c);
     if (a.cold)  // swift_convert, ammonia.pyx:280-286
         trot = trot / (1.0 + (trot / 41.18) * log(1.0 + 0.6 * exp(-15.7 / trot)));
@@ -169,7 +189,8 @@ __device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC>
     const double frac = my_para ? 1.0 - orth : orth;
     const double pop = exp10(ntot) * frac * zlev / qtot;          // ammonia.pyx:353
     const double e = exp(-sm.hnu_k / tex);                        // ammonia.pyx:354-357
-    const double tau_main = pop * sm.fracterm * ((1.0 - e) / (1.0 + e)) * (sm.width_c / sigm);
+    tau_main = pop * sm.fracterm * ((1.0 - e) / (1.0 + e)) * (sm.width_c / sigm);
+    }
     // T_B amplitude T0_j * (G(T0_j/tex) - tbg_j), hyperfine.pyx:106-113, as the max of two
     // lines in j: the reference's G is a convex piecewise-linear table, so this reproduces
     // the table lerp -- including a knot inside the band -- without per-channel look-ups.
@@ -255,7 +276,7 @@ __device__ __forceinline__ void nh3_pair_term(float &tp, uint32_t ra, uint64_t x
 // ---- the fused kernel ---------------------------------------------------------
 // WRITE_PRED = false: log-likelihood against the pixel's data (a.data, a.lnL);
 // WRITE_PRED = true : model spectra only (a.pred), no data are read.
-template <int NC, bool WRITE_PRED, typename PT>
+template <int MODEL, int NC, bool WRITE_PRED, typename PT>
 __global__ void __launch_bounds__(NF_THREADS, (NC <= 3 ? 4 : 3))
 nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 {
@@ -267,10 +288,13 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // pair[c][p][q] holds lines (2q+p, 2q+p+1); npair pairs per parity
     const int npair = a.npair;
-    const size_t warp_bytes = (size_t)NC * 2 * npair * sizeof(Nh3Pair) + sizeof(Scratch);
+    const int nkey = a.nkey;                               // line keys per component (multiple of 4)
+    const size_t pair_bytes = (size_t)NC * 2 * npair * sizeof(Nh3Pair), key_bytes = (size_t)NC * nkey * sizeof(short2);
+    const size_t warp_bytes = pair_bytes + key_bytes + sizeof(Scratch);
     unsigned char *wbase = smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128 + warp * warp_bytes;
     float *pairf = reinterpret_cast<float *>(wbase);
-    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + (size_t)NC * 2 * npair * sizeof(Nh3Pair));
+    short2 *keys = reinterpret_cast<short2 *>(wbase + pair_bytes);   // per line: first chunk, first chunk after its window
+    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + pair_bytes + key_bytes);
     uint32_t *cw = reinterpret_cast<uint32_t *>(sc.tab);   // cnt[c][g] = cw[c * 36 + g]
     const uint32_t pair_addr = smem_u32(pairf);
 
@@ -304,7 +328,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 
     for (int64_t bb = b0 + (int64_t)warp * vpw; bb < bw_end; bb += vb) {
         const int nb = (int)min((int64_t)vb, bw_end - bb);
-        nh3_setup_batch<NC, PT>(a, sc, bb, nb, lane);
+        nh3_setup_batch<MODEL, NC, PT>(a, sc, bb, nb, lane);
         __syncwarp();
 
         for (int k = 0; k < nb; ++k) {
@@ -363,7 +387,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                             hh = 0.5f * (float)(hi - 1 - lo);
                         }
                         if (act) {
-                            sc.key[c][i] = make_short2((short)kE, (short)kF);
+                            keys[c * nkey + i] = make_short2((short)kE, (short)kF);
                             atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u);          // table counts of super-block 0
                             atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x10000u);
                             // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
@@ -407,7 +431,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                                     if (NC > 2) c += t >= 2 * NL;
                                     if (NC > 3) c += t >= 3 * NL;
                                     const int i = t - c * NL;
-                                    const short2 ky = sc.key[c][i];
+                                    const short2 ky = keys[c * nkey + i];
                                     atomicAdd(&cw[c * 36 + min(max((int)ky.x - sb, 0), 32)], 1u);
                                     atomicAdd(&cw[c * 36 + min(max((int)ky.y - sb, 0), 32)], 0x10000u);
                                 }
@@ -503,18 +527,21 @@ template <int NC>
 static size_t nh3_smem_bytes(const NfLikeArgs &a)
 {
     const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
-    return 128 + data + ((size_t)NC * 2 * a.npair * sizeof(Nh3Pair) + sizeof(Nh3Scratch<NC>)) * NH3_WARPS;
+    return 128 + data + ((size_t)NC * 2 * a.npair * sizeof(Nh3Pair) + (size_t)NC * a.nkey * sizeof(short2) +
+                         sizeof(Nh3Scratch<NC>)) * NH3_WARPS;
 }
 
-template <int NC, bool WP, typename PT>
+template <int MODEL, int NC, bool WP, typename PT>
 static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
 {
     NfLikeArgs a = a0;
     int max_lines = 1;
     for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
     a.npair = (max_lines >> 1) + 1;     // lines 0..NL (NL = the null line) in pairs of either parity
-    auto kern = nf_nh3_kernel<NC, WP, PT>;
+    a.nkey = (max_lines + 3) & ~3;
+    auto kern = nf_nh3_kernel<MODEL, NC, WP, PT>;
     const size_t smem = nh3_smem_bytes<NC>(a);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
@@ -524,13 +551,13 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int NC>
+template <int MODEL, int NC>
 static cudaError_t nh3_launch_nc(const NfLikeArgs &a, cudaStream_t st)
 {
     const bool wp = a.pred != nullptr;
     if (a.param_f64)
-        return wp ? nh3_launch_one<NC, true, double>(a, st) : nh3_launch_one<NC, false, double>(a, st);
-    return wp ? nh3_launch_one<NC, true, float>(a, st) : nh3_launch_one<NC, false, float>(a, st);
+        return wp ? nh3_launch_one<MODEL, NC, true, double>(a, st) : nh3_launch_one<MODEL, NC, false, double>(a, st);
+    return wp ? nh3_launch_one<MODEL, NC, true, float>(a, st) : nh3_launch_one<MODEL, NC, false, float>(a, st);
 }
 
 cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st);
@@ -542,10 +569,24 @@ cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st)
     cudaError_t e = nh3_init_device_tables();
     if (e) return e;
     switch (a.ncomp) {
-    case 1: return nh3_launch_nc<1>(a, st);
-    case 2: return nh3_launch_nc<2>(a, st);
-    case 3: return nh3_launch_nc<3>(a, st);
-    case 4: return nh3_launch_nc<4>(a, st);
+    case 1: return nh3_launch_nc<0, 1>(a, st);
+    case 2: return nh3_launch_nc<0, 2>(a, st);
+    case 3: return nh3_launch_nc<0, 3>(a, st);
+    case 4: return nh3_launch_nc<0, 4>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// N2H+ (diazenylium.pyx): same hyperfine kernel, 4-parameter front end
+cudaError_t nf_launch_n2hp(const NfLikeArgs &a, cudaStream_t st)
+{
+    cudaError_t e = nh3_init_device_tables();
+    if (e) return e;
+    switch (a.ncomp) {
+    case 1: return nh3_launch_nc<1, 1>(a, st);
+    case 2: return nh3_launch_nc<1, 2>(a, st);
+    case 3: return nh3_launch_nc<1, 3>(a, st);
+    case 4: return nh3_launch_nc<1, 4>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -663,7 +663,8 @@ int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_
         a.spec[k] = px->spec[k];
         if (px->spec[k].para) a.need_para = 1; else a.need_ortho = 1;
     }
-    NS_CUDA(px->model == NF_MODEL_NH3 ? nf_launch_nh3(a, s->stream) : nf_launch_gauss(a, s->stream));
+    NS_CUDA(px->model == NF_MODEL_NH3 ? nf_launch_nh3(a, s->stream)
+            : px->model == NF_MODEL_N2HP ? nf_launch_n2hp(a, s->stream) : nf_launch_gauss(a, s->stream));
     s->launches += 2;
     return NF_OK;
 }
@@ -682,11 +683,11 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     *out = nullptr;
     if (!px || !pr || !cfg || !pix_ids || !nlive || n_run < 1 || ncomp < 1) return NF_EINVAL;
     if (px->device != pr->device) return NF_EINVAL;
-    const int n_model = px->model == NF_MODEL_NH3 ? 6 : 3;
+    const int n_model = px->model == NF_MODEL_NH3 ? 6 : (px->model == NF_MODEL_N2HP ? 4 : 3);
     if (pr->n_model != n_model) return NF_EINVAL;
     const int ndim = n_model * ncomp;
     if (ndim > NS_MAX_DIM) return NF_EINVAL;
-    if (px->model == NF_MODEL_NH3 && ncomp > NF_MAX_NCOMP_NH3) return NF_EINVAL;
+    if (px->model != NF_MODEL_GAUSS && ncomp > NF_MAX_NCOMP_NH3) return NF_EINVAL;
     if (cfg->nlive_max < 8 || cfg->n_prop < 1 || cfg->max_samples < 2 * cfg->nlive_max || !(cfg->tol > 0.0) ||
         !(cfg->efr > 0.0 && cfg->efr <= 1.0) || cfg->max_iter < 1)
         return NF_EINVAL;

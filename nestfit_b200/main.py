@@ -256,8 +256,8 @@ class CubeFitter:
             vidx = np.flatnonzero(valid)
             dv = data[vidx]
             xarrs = [c.xarr for c in self.stack.cubes]
-            if model == 'ammonia':
-                blk = PixelBlock('ammonia', xarrs, dv, noise[vidx], trans_ids=[c.trans_id for c in self.stack.cubes],
+            if model in ('ammonia', 'diazenylium'):
+                blk = PixelBlock(model, xarrs, dv, noise[vidx], trans_ids=[c.trans_id for c in self.stack.cubes],
                                  device=device)
             else:
                 blk = PixelBlock('gaussian', xarrs, dv, noise[vidx],

@@ -1,4 +1,4 @@
-from . import ammonia, gaussian
+from . import ammonia, diazenylium, gaussian
 
-MODEL_MODULES = [ammonia, gaussian]
+MODEL_MODULES = [ammonia, gaussian, diazenylium]
 MODELS = {m.NAME: m for m in MODEL_MODULES}

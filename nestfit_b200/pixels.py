@@ -17,17 +17,18 @@ from . import _lib
 class PixelBlock:
     def __init__(self, model, xarrs, data, noise, trans_ids=None, rest_freq=None, device=0):
         """
-        model     : 'ammonia' | 'gaussian'
+        model     : 'ammonia' | 'gaussian' | 'diazenylium'
         xarrs     : sequence of n_spec ascending uniform frequency axes [Hz], equal length
         data      : array [n_pix, n_spec, n_chan] (float32 or float64)
         noise     : array [n_pix, n_spec] rms per spectrum
-        trans_ids : NH3 transition ids (1..9) per spectrum
+        trans_ids : NH3 transition ids (1..9) / N2H+ transition ids (1..3) per spectrum
         rest_freq : Gaussian-model rest frequency [Hz]
         """
         from .core import check_uniform_axis
         lib = _lib.load()
         self.model_name = model
-        self.model = {"ammonia": _lib.NF_MODEL_NH3, "gaussian": _lib.NF_MODEL_GAUSS}[model]
+        self.model = {"ammonia": _lib.NF_MODEL_NH3, "gaussian": _lib.NF_MODEL_GAUSS,
+                      "diazenylium": _lib.NF_MODEL_N2HP}[model]
         xarrs = [np.ascontiguousarray(x, dtype=np.float64) for x in xarrs]
         self.n_spec = len(xarrs)
         self.n_chan = int(xarrs[0].shape[0])
@@ -49,7 +50,7 @@ class PixelBlock:
         nu_chan = np.array([x[1] - x[0] for x in xarrs], dtype=np.float64)
         tid = None
         rf = None
-        if self.model == _lib.NF_MODEL_NH3:
+        if self.model in (_lib.NF_MODEL_NH3, _lib.NF_MODEL_N2HP):
             tid = np.ascontiguousarray(trans_ids, dtype=np.int32)
             if tid.shape != (self.n_spec,):
                 raise ValueError("trans_ids must have one entry per spectrum")
@@ -64,7 +65,7 @@ class PixelBlock:
                                         _lib.ptr(data), dtype, _lib.ptr(noise), C.byref(out)),
                    "nf_pixels_create")
         self.handle = out
-        self.n_model = 6 if self.model == _lib.NF_MODEL_NH3 else 3
+        self.n_model = {_lib.NF_MODEL_NH3: 6, _lib.NF_MODEL_N2HP: 4, _lib.NF_MODEL_GAUSS: 3}[self.model]
 
     def close(self):
         if getattr(self, "handle", None):
@@ -115,6 +116,9 @@ class PixelBlock:
             flags = (_lib.NF_FLAG_COLD if cold else 0) | (_lib.NF_FLAG_LTE if lte else 0)
             rc = lib.nf_nh3_loglike_host(self.handle, _lib.ptr(params), dt, _lib.ptr(pv), vecs_per_pix, B,
                                          ncomp, flags, _lib.ptr(out))
+        elif self.model == _lib.NF_MODEL_N2HP:
+            rc = lib.nf_n2hp_loglike_host(self.handle, _lib.ptr(params), dt, _lib.ptr(pv), vecs_per_pix, B,
+                                          ncomp, _lib.ptr(out))
         else:
             rc = lib.nf_gauss_loglike_host(self.handle, _lib.ptr(params), dt, _lib.ptr(pv), vecs_per_pix, B,
                                            ncomp, _lib.ptr(out))
@@ -132,6 +136,8 @@ class PixelBlock:
         if self.model == _lib.NF_MODEL_NH3:
             flags = (_lib.NF_FLAG_COLD if cold else 0) | (_lib.NF_FLAG_LTE if lte else 0)
             rc = lib.nf_nh3_predict_host(self.handle, _lib.ptr(params), dt, B, ncomp, flags, _lib.ptr(out))
+        elif self.model == _lib.NF_MODEL_N2HP:
+            rc = lib.nf_n2hp_predict_host(self.handle, _lib.ptr(params), dt, B, ncomp, _lib.ptr(out))
         else:
             rc = lib.nf_gauss_predict_host(self.handle, _lib.ptr(params), dt, B, ncomp, _lib.ptr(out))
         _lib.check(rc, "predict")

@@ -1,0 +1,262 @@
+"""Store post-processing on the predict kernel: host mirror of the aggregation
+steps the reference runs after a cube fit (nestfit/main.py:664-1061) and, batched
+on the GPU, of its two per-pixel ``runner.predict`` loops
+
+    deblend_hf_intensity          nestfit/main.py:1064-1133
+    generate_predicted_profiles   nestfit/main.py:1136-1193
+
+The reference walks (lon, lat, component) in Python and calls ``runner.predict``
+once per triple (main.py:1106-1113, 1182-1188).  Here the MAP-parameter cube is
+flattened to one batch of single-component vectors and scored by one launch of
+``nf_nh3_predict`` per chunk of vectors; array shapes, dataset names and axis
+orders written to the store are the reference's.
+"""
+import numpy as np
+
+from .main import nans
+
+
+# ---------------------------------------------------------------------------
+# aggregation of per-pixel run groups into dense arrays (host side, numpy)
+# ---------------------------------------------------------------------------
+def aggregate_run_attributes(store):
+    """'nbest' (b, l) and 'evidence', 'evidence_err', 'AIC', 'AICc', 'BIC' (m, b, l)
+    (main.py:664-721)."""
+    hdf, dpath = store.hdf, store.dpath
+    n_lon, n_lat = int(hdf.attrs['naxis1']), int(hdf.attrs['naxis2'])
+    ncomp_max = int(hdf.attrs['n_max_components'])
+    shape = (n_lon, n_lat, ncomp_max + 1)
+    lnz, lnzerr, bic, aic, aicc = (nans(shape) for _ in range(5))
+    nb = np.full((n_lon, n_lat), -1, dtype=np.int32)
+    for group in store.iter_pix_groups():
+        i_lon, i_lat = int(group.attrs['i_lon']), int(group.attrs['i_lat'])
+        nb[i_lon, i_lat] = group.attrs['nbest']
+        for model in group:
+            subg = group[model]
+            ncomp = int(subg.attrs['ncomp'])
+            if ncomp == 1:
+                lnz[i_lon, i_lat, 0] = subg.attrs['null_lnZ']
+                bic[i_lon, i_lat, 0] = subg.attrs['null_BIC']
+                aic[i_lon, i_lat, 0] = subg.attrs['null_AIC']
+                aicc[i_lon, i_lat, 0] = subg.attrs['null_AICc']
+            lnz[i_lon, i_lat, ncomp] = subg.attrs['global_lnZ']
+            lnzerr[i_lon, i_lat, ncomp] = subg.attrs['global_lnZ_err']
+            bic[i_lon, i_lat, ncomp] = subg.attrs['BIC']
+            aic[i_lon, i_lat, ncomp] = subg.attrs['AIC']
+            aicc[i_lon, i_lat, ncomp] = subg.attrs['AICc']
+    store.create_dataset('nbest', nb.transpose(), group=dpath)
+    store.create_dataset('evidence', lnz.transpose(), group=dpath)
+    store.create_dataset('evidence_err', lnzerr.transpose(), group=dpath)
+    store.create_dataset('BIC', bic.transpose(), group=dpath)
+    store.create_dataset('AIC', aic.transpose(), group=dpath)
+    store.create_dataset('AICc', aicc.transpose(), group=dpath)
+
+
+def gaussian_kernel2d(sigma):
+    """Normalised 2-D Gaussian on an odd (8 sigma + 1) grid: astropy's
+    ``Gaussian2DKernel(sigma)`` default support."""
+    half = max(1, int(np.ceil(4 * sigma)))
+    ax = np.arange(-half, half + 1)
+    k = np.exp(-0.5 * (ax[:, None]**2 + ax[None, :]**2) / sigma**2)
+    return k / k.sum()
+
+
+def convolve_nan_extend(img, kernel):
+    """2-D convolution with edge replication ('extend') in which NaN pixels are
+    interpolated over by renormalising the kernel -- the semantics of
+    ``astropy.convolution.convolve(img, kernel, boundary='extend')`` that
+    `convolve_evidence` relies on (main.py:752-753)."""
+    img = np.asarray(img, dtype=np.float64)
+    ky, kx = kernel.shape
+    py, px = ky // 2, kx // 2
+    pad = np.pad(img, ((py, py), (px, px)), mode='edge')
+    good = np.isfinite(pad)
+    vals = np.where(good, pad, 0.0)
+    num = np.zeros_like(img)
+    den = np.zeros_like(img)
+    for dy in range(ky):
+        for dx in range(kx):
+            w = kernel[ky - 1 - dy, kx - 1 - dx]
+            if w == 0.0:
+                continue
+            num += w * vals[dy:dy + img.shape[0], dx:dx + img.shape[1]]
+            den += w * good[dy:dy + img.shape[0], dx:dx + img.shape[1]]
+    with np.errstate(invalid='ignore', divide='ignore'):
+        out = num / den * kernel.sum()
+    out[den == 0] = np.nan
+    return out
+
+
+def convolve_evidence(store, kernel):
+    """'conv_evidence' (m, b, l) and 'conv_nbest' (b, l) (main.py:724-774).  `kernel`:
+    2-D array or the standard deviation in pixels of a Gaussian kernel."""
+    if isinstance(kernel, (int, float)):
+        kernel = gaussian_kernel2d(float(kernel))
+    kernel = np.asarray(kernel, dtype=np.float64)
+    hdf, dpath = store.hdf, store.dpath
+    ncomp_max = int(hdf.attrs['n_max_components'])
+    lnZ_thresh = hdf.attrs['lnZ_threshold']
+    data = np.asarray(hdf[f'{dpath}/evidence'][...])
+    nbest = np.asarray(hdf[f'{dpath}/nbest'][...])
+    cdata = np.zeros_like(data)
+    for i in range(data.shape[0]):
+        cdata[i] = convolve_nan_extend(data[i], kernel)
+    conv_nbest = np.zeros(cdata[0].shape, dtype=np.int32)
+    for i in range(ncomp_max):
+        with np.errstate(invalid='ignore'):
+            conv_nbest[(conv_nbest == i) & (cdata[i + 1] - cdata[i] > lnZ_thresh)] += 1
+    conv_nbest[nbest == -1] = -1
+    overshot = conv_nbest - nbest >= 2       # a jump of +2 has no model run behind it
+    conv_nbest[overshot] = nbest[overshot] + 1
+    store.create_dataset('conv_nbest', conv_nbest, group=dpath)
+    store.create_dataset('conv_evidence', cdata, group=dpath)
+
+
+def aggregate_run_products(store):
+    """'marg_quantiles' (M), 'nbest_MAP' / 'nbest_bestfit' (m, p, b, l) and
+    'nbest_marginals' (m, p, M, b, l) (main.py:819-882).  Uses 'conv_nbest' when the
+    evidence was convolved, else the per-pixel 'nbest'."""
+    hdf, dpath = store.hdf, store.dpath
+    n_lon, n_lat = int(hdf.attrs['naxis1']), int(hdf.attrs['naxis2'])
+    key = 'conv_nbest' if f'{dpath}/conv_nbest' in hdf else 'nbest'
+    nbest_data = np.asarray(hdf[f'{dpath}/{key}'][...]).transpose()
+    ncomp_max = int(hdf.attrs['n_max_components'])
+    n_params = int(hdf.attrs['n_params'])
+    marg_quan = np.asarray(store.find_first_valid_group().attrs['marg_quantiles'])
+    n_margs = len(marg_quan)
+    mapdata = nans((n_lon, n_lat, n_params, ncomp_max))
+    bfdata = nans((n_lon, n_lat, n_params, ncomp_max))
+    pardata = nans((n_lon, n_lat, n_margs, n_params, ncomp_max))
+    for group in store.iter_pix_groups():
+        i_lon, i_lat = int(group.attrs['i_lon']), int(group.attrs['i_lat'])
+        nbest = int(nbest_data[i_lon, i_lat])
+        if nbest <= 0 or f'{nbest}' not in group:
+            continue
+        nb_group = group[f'{nbest}']
+        p_shape = (n_params, nbest)
+        mapdata[i_lon, i_lat, :, :nbest] = np.asarray(nb_group['map_params'][...]).reshape(p_shape)
+        bfdata[i_lon, i_lat, :, :nbest] = np.asarray(nb_group['bestfit_params'][...]).reshape(p_shape)
+        pardata[i_lon, i_lat, :, :, :nbest] = np.asarray(nb_group['marginals'][...]).reshape((n_margs,) + p_shape)
+    store.create_dataset('marg_quantiles', marg_quan, group=dpath)
+    store.create_dataset('nbest_MAP', mapdata.transpose(), group=dpath)
+    store.create_dataset('nbest_bestfit', bfdata.transpose(), group=dpath)
+    store.create_dataset('nbest_marginals', pardata.transpose(), group=dpath)
+
+
+def aggregate_run_pdfs(store, par_bins=None):
+    """'pdf_bins' (p, h) and 'post_pdfs' (r, m, p, h, b, l) (main.py:885-953)."""
+    hdf, dpath = store.hdf, store.dpath
+    n_lon, n_lat = int(hdf.attrs['naxis1']), int(hdf.attrs['naxis2'])
+    ncomp_max = int(hdf.attrs['n_max_components'])
+    n_params = int(hdf.attrs['n_params'])
+    if par_bins is None:
+        n_bins = 200
+        margdata = np.asarray(hdf[f'{dpath}/nbest_marginals'][...])
+        vmins = np.nanmin(margdata[:, :, 0, :, :], axis=(0, 2, 3))
+        vmaxs = np.nanmax(margdata[:, :, 8, :, :], axis=(0, 2, 3))
+        par_bins = np.array([np.linspace(lo, hi, n_bins) for lo, hi in zip(vmins, vmaxs)])
+    else:
+        par_bins = np.asarray(par_bins)
+        n_bins = par_bins.shape[1]
+    histdata = nans((n_lon, n_lat, ncomp_max, n_params, ncomp_max, n_bins - 1))
+    for group in store.iter_pix_groups():
+        i_l, i_b = int(group.attrs['i_lon']), int(group.attrs['i_lat'])
+        for i_r in range(ncomp_max):
+            n_run = i_r + 1
+            if f'{n_run}' not in group or 'posteriors' not in group[f'{n_run}']:
+                continue
+            post = np.asarray(group[f'{n_run}']['posteriors'][...])
+            for i_p, bins in enumerate(par_bins):
+                for i_m in range(n_run):
+                    hist, _ = np.histogram(post[:, i_p * n_run + i_m], bins=bins)
+                    histdata[i_l, i_b, i_r, i_p, i_m, :] = hist
+    with np.errstate(invalid='ignore', divide='ignore'):
+        histdata /= np.nansum(histdata, axis=5, keepdims=True)
+    bin_mids = (par_bins[:, :-1] + par_bins[:, 1:]) / 2
+    store.create_dataset('pdf_bins', bin_mids, group=dpath)
+    store.create_dataset('post_pdfs', histdata.transpose((2, 4, 3, 5, 1, 0)).astype('float32'), group=dpath)
+
+
+# ---------------------------------------------------------------------------
+# batched predict loops
+# ---------------------------------------------------------------------------
+def _runner_block(runner):
+    blk = getattr(runner, '_block', None)
+    if blk is None:
+        raise TypeError('runner must be a nestfit_b200 Runner (it owns the device pixel block)')
+    return blk
+
+
+def predict_map_cube(pmap, runner, chunk=32768, want_spectra=False):
+    """Model every non-NaN single-component MAP vector of `pmap` (l, b, p, m) with one
+    predict launch per `chunk` vectors.  Returns (peak, sum) of shape (l, b, m, t)
+    and, if `want_spectra`, the spectra as a list over transitions of (l, b, m, S)."""
+    assert runner.ncomp == 1
+    blk = _runner_block(runner)
+    n_l, n_b, n_p, n_m = pmap.shape
+    vec = np.ascontiguousarray(pmap.transpose(0, 1, 3, 2).reshape(-1, n_p))      # (l, b, m) x p
+    ok = np.flatnonzero(~np.isnan(vec).any(axis=1))
+    n_t = blk.n_spec
+    pk = nans((n_l * n_b * n_m, n_t))
+    sm = nans((n_l * n_b * n_m, n_t))
+    spectra = [nans((n_l * n_b * n_m, blk.n_chan)) for _ in range(n_t)] if want_spectra else None
+    kw = {k: getattr(runner, k) for k in ('cold', 'lte') if hasattr(runner, k)}
+    for c0 in range(0, ok.size, chunk):
+        ix = ok[c0:c0 + chunk]
+        pred = blk.predict(np.ascontiguousarray(vec[ix]), 1, **kw)               # [B, t, S]
+        pk[ix] = np.nanmax(pred, axis=2)
+        sm[ix] = np.nansum(pred, axis=2, dtype=np.float64)
+        if want_spectra:
+            for t in range(n_t):
+                spectra[t][ix] = pred[:, t, :]
+    shape = (n_l, n_b, n_m, n_t)
+    if want_spectra:
+        spectra = [s.reshape(n_l, n_b, n_m, -1) for s in spectra]
+    return pk.reshape(shape), sm.reshape(shape), spectra
+
+
+def deblend_hf_intensity(store, stack, runner):
+    """'peak_intensity', 'integrated_intensity' (t, m, b, l) and 'hf_deblended'
+    (t, m, S, b, l) from the MAP parameters (main.py:1064-1133)."""
+    hdf, dpath = store.hdf, store.dpath
+    bins = np.asarray(hdf[f'{dpath}/pdf_bins'][...])
+    pmap = np.asarray(hdf[f'{dpath}/nbest_MAP'][...]).transpose()                # (l, b, p, m)
+    pkint, intint, _ = predict_map_cube(pmap, runner)
+    for i_t, cube in enumerate(stack.cubes):       # K -> K km/s
+        intint[:, :, :, i_t] *= cube.dv
+    dv_bin = abs(bins[0, 1] - bins[0, 0])
+    vaxis = bins[0].reshape(1, 1, 1, 1, -1)
+    model = store.model
+    if model is None:                  # store opened before the model metadata was inserted
+        from .models import MODELS
+        model = MODELS[hdf.attrs['model_name']]
+    vcen = np.expand_dims(pmap[:, :, model.IX_VCEN, :], (3, 4))
+    sigm = np.expand_dims(pmap[:, :, model.IX_SIGM, :], (3, 4))
+    norm_fact = dv_bin / (sigm * np.sqrt(2 * np.pi))
+    hfdb = norm_fact * intint[..., np.newaxis] * np.exp(-0.5 * ((vaxis - vcen) / sigm)**2)
+    store.create_dataset('peak_intensity', pkint.transpose(), group=dpath)
+    store.create_dataset('integrated_intensity', intint.transpose(), group=dpath)
+    store.create_dataset('hf_deblended', hfdb.transpose((3, 2, 4, 1, 0)).astype('float32'), group=dpath)
+
+
+def generate_predicted_profiles(store, stack, runner):
+    """'model_spec/trans<TRANS_ID>' (m, S, b, l): MAP model profiles per transition
+    (main.py:1136-1193)."""
+    hdf, dpath = store.hdf, store.dpath
+    pmap = np.asarray(hdf[f'{dpath}/nbest_MAP'][...]).transpose()
+    _, _, spectra = predict_map_cube(pmap, runner, want_spectra=True)
+    for mcube, dcube in zip(spectra, stack):
+        store.create_dataset(f'trans{dcube.trans_id}', mcube.transpose((2, 3, 1, 0)).astype('float32'),
+                             group=f'{dpath}/model_spec')
+
+
+def postprocess_run(store, stack, runner, par_bins=None, evid_kernel=None):
+    """The reference's `postprocess_run` sequence (main.py:1240-1272) for the steps built
+    here; the PDF convolution / quantisation steps stay with the reference."""
+    aggregate_run_attributes(store)
+    if evid_kernel is not None:
+        convolve_evidence(store, evid_kernel)
+    aggregate_run_products(store)
+    aggregate_run_pdfs(store, par_bins=par_bins)
+    deblend_hf_intensity(store, stack, runner)
+    generate_predicted_profiles(store, stack, runner)

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "../include/nf_nh3_tables.h"
+#include "../include/nf_n2hp_tables.h"
 #include "../include/nf_priors.h"
 
 /* includes/model_includes.pxi:27-36 */
@@ -37,6 +38,11 @@ static const int NH3_OFF[NF_NH3_NTRANS + 1] = NF_NH3_LINE_OFFSET_INIT;
 static const int NH3_PARA[NF_NH3_NTRANS] = NF_NH3_IS_PARA_INIT;
 static const double NH3_VOFF[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_VOFF_INIT;
 static const double NH3_WT[NF_NH3_NLINES_TOTAL] = NF_NH3_LINE_WEIGHT_INIT;
+/* nestfit/models/diazenylium.pyx:31-92 */
+static const double N2HP_NU[NF_N2HP_NTRANS] = NF_N2HP_REST_FREQ_INIT;
+static const int N2HP_OFF[NF_N2HP_NTRANS + 1] = NF_N2HP_LINE_OFFSET_INIT;
+static const double N2HP_VOFF[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_VOFF_INIT;
+static const double N2HP_WT[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_WEIGHT_INIT;
 
 /* ------------------------------------------------------------------------ */
 /* exp(-x) with the semantics of LIME's FastExp(const float)                 */
@@ -135,21 +141,21 @@ void nfo_tbg(const double *xarr, long n, double *tbg)
 /* `tarr` is scratch [n]; `pred` is accumulated into.  counters[0] += number  */
 /* of windowed Gaussian evaluations, counters[1] += radiative-transfer        */
 /* channels (SURVEY.md 8d work accounting); may be NULL.                      */
-static void hf_predict(const double *xarr, const double *tbg, long n, int t,
-                       double voff, double tex, double ltau_main, double sigm,
-                       double *tarr, double *pred, int64_t *counters)
+static void hf_predict_lines(const double *xarr, const double *tbg, long n, double nu0,
+                             const double *line_voff, const double *line_wt, long nlines,
+                             double voff, double tex, double ltau_main, double sigm,
+                             double *tarr, double *pred, int64_t *counters)
 {
-    const double nu0 = NH3_NU[t];
     const double nu_min = xarr[0], nu_chan = xarr[1] - xarr[0]; /* core.pyx:503,513 */
     double tau_main = pow(10.0, ltau_main);                      /* hyperfine.pyx:63 */
     long i, j, lo, hi;
     for (j = 0; j < n; j++) tarr[j] = 0.0;
-    for (i = NH3_OFF[t]; i < NH3_OFF[t + 1]; i++) {
-        double hf_freq = (1.0 - NH3_VOFF[i] / NFO_CKMS) * nu0;
+    for (i = 0; i < nlines; i++) {
+        double hf_freq = (1.0 - line_voff[i] / NFO_CKMS) * nu0;
         double hf_width = sigm / NFO_CKMS * hf_freq;
         double hf_offset = voff / NFO_CKMS * hf_freq;
         double hf_nucen = hf_freq - hf_offset;
-        double hf_tau = tau_main * NH3_WT[i];
+        double hf_tau = tau_main * line_wt[i];
         double hf_idenom = 0.5 / (hf_width * hf_width);
         double nu_cutoff = sqrt(12.5 / hf_idenom);               /* hyperfine.pyx:82 */
         double nu_lo = hf_nucen - nu_min - nu_cutoff;
@@ -173,6 +179,29 @@ static void hf_predict(const double *xarr, const double *tbg, long n, int t,
                  * (1.0 - nfo_fast_expn(tarr[j]));
         if (counters) counters[1] += 1;
     }
+}
+
+static void hf_predict(const double *xarr, const double *tbg, long n, int t,
+                       double voff, double tex, double ltau_main, double sigm,
+                       double *tarr, double *pred, int64_t *counters)
+{
+    hf_predict_lines(xarr, tbg, n, NH3_NU[t], NH3_VOFF + NH3_OFF[t], NH3_WT + NH3_OFF[t],
+                     NH3_OFF[t + 1] - NH3_OFF[t], voff, tex, ltau_main, sigm, tarr, pred, counters);
+}
+
+/* nestfit/models/diazenylium.pyx:140-154: params (voff, tex, ltau, sigm), parameter-major;
+ * trans_id 1..3 = J 1-0, 2-1, 3-2. */
+void nfo_nnhp_predict(const double *xarr, const double *tbg, long n, int trans_id,
+                      const double *params, long ncomp, double *tarr, double *pred,
+                      int64_t *counters)
+{
+    const int t = trans_id - 1;
+    long c, j;
+    for (j = 0; j < n; j++) pred[j] = 0.0;
+    for (c = 0; c < ncomp; c++)
+        hf_predict_lines(xarr, tbg, n, N2HP_NU[t], N2HP_VOFF + N2HP_OFF[t], N2HP_WT + N2HP_OFF[t],
+                         N2HP_OFF[t + 1] - N2HP_OFF[t], params[c], params[ncomp + c],
+                         params[2 * ncomp + c], params[3 * ncomp + c], tarr, pred, counters);
 }
 
 /* nestfit/models/ammonia.pyx:326-361.  trans_id is 1-based ((1,1) -> 1). */
@@ -266,6 +295,38 @@ int nfo_nh3_loglike_batch(long nspec, long nchan, const double *xarr,
         for (s = 0; s < nspec; s++) {
             nfo_amm_predict(xarr + s * nchan, tbg + s * nchan, nchan, trans_id[s],
                             params + b * 6 * ncomp, ncomp, cold, lte, tarr, pred, counters);
+            if (data)
+                acc += nfo_loglike(data + (p * nspec + s) * nchan, pred, nchan,
+                                   noise[p * nspec + s]);
+            if (pred_out)
+                memcpy(pred_out + (b * nspec + s) * nchan, pred, sizeof(double) * nchan);
+        }
+        if (lnL) lnL[b] = acc;
+    }
+    free(tbg); free(tarr); free(pred);
+    return 0;
+}
+
+/* DiazenyliumRunner.c_loglikelihood (diazenylium.pyx:206-215) minus the transform:
+ * params [B][4*ncomp]. */
+int nfo_n2hp_loglike_batch(long nspec, long nchan, const double *xarr,
+                           const int *trans_id, const double *data,
+                           const double *noise, const double *params,
+                           const int *pix_of_vec, long B, long ncomp,
+                           double *lnL, double *pred_out, int64_t *counters)
+{
+    double *tbg = (double *)malloc(sizeof(double) * nspec * nchan);
+    double *tarr = (double *)malloc(sizeof(double) * nchan);
+    double *pred = (double *)malloc(sizeof(double) * nchan);
+    long b, s;
+    if (!tbg || !tarr || !pred) { free(tbg); free(tarr); free(pred); return -1; }
+    for (s = 0; s < nspec; s++) nfo_tbg(xarr + s * nchan, nchan, tbg + s * nchan);
+    for (b = 0; b < B; b++) {
+        long p = pix_of_vec ? pix_of_vec[b] : 0;
+        double acc = 0.0;
+        for (s = 0; s < nspec; s++) {
+            nfo_nnhp_predict(xarr + s * nchan, tbg + s * nchan, nchan, trans_id[s],
+                             params + b * 4 * ncomp, ncomp, tarr, pred, counters);
             if (data)
                 acc += nfo_loglike(data + (p * nspec + s) * nchan, pred, nchan,
                                    noise[p * nspec + s]);

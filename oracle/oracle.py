@@ -78,6 +78,34 @@ def nh3_batch(xarrs, trans_ids, params, ncomp, data=None, noise=None, pix_of_vec
     return dict(lnL=lnL, pred=pred, counters=counters)
 
 
+N2HP_NU = [93173.7637e6, 186344.8420e6, 279511.8325e6]     # diazenylium.pyx:39-43
+
+
+def n2hp_batch(xarrs, trans_ids, params, ncomp, data=None, noise=None, pix_of_vec=None, want_pred=False,
+               count=False):
+    """N2H+ (diazenylium) model: params [B, 4*ncomp] = (voff, tex, ltau, sigm), parameter-major."""
+    lib = load()
+    x = np.ascontiguousarray(xarrs, dtype=np.float64)
+    nspec, nchan = x.shape
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    B = params.shape[0]
+    assert params.shape[1] == 4 * ncomp
+    tid = np.ascontiguousarray(trans_ids, dtype=np.int32)
+    d = n = None
+    lnL = None
+    if data is not None:
+        d = np.ascontiguousarray(data, dtype=np.float64)
+        n = np.ascontiguousarray(np.broadcast_to(np.asarray(noise, dtype=np.float64), d.shape[:2]))
+        lnL = np.empty(B, dtype=np.float64)
+    pv = None if pix_of_vec is None else np.ascontiguousarray(pix_of_vec, dtype=np.int32)
+    pred = np.empty((B, nspec, nchan), dtype=np.float64) if want_pred else None
+    counters = np.zeros(2, dtype=np.int64) if count else None
+    rc = lib.nfo_n2hp_loglike_batch(C.c_long(nspec), C.c_long(nchan), _p(x), _p(tid), _p(d), _p(n), _p(params),
+                                    _p(pv), C.c_long(B), C.c_long(ncomp), _p(lnL), _p(pred), _p(counters))
+    assert rc == 0
+    return dict(lnL=lnL, pred=pred, counters=counters)
+
+
 def gauss_batch(xarr, rest_freq, params, ncomp, data=None, noise=None, pix_of_vec=None,
                 want_pred=False, count=False):
     lib = load()

@@ -45,11 +45,13 @@ def load():
     hyperfine = importlib.import_module("nestfit.models.hyperfine")
     ammonia = importlib.import_module("nestfit.models.ammonia")
     gaussian = importlib.import_module("nestfit.models.gaussian")
+    diazenylium = importlib.import_module("nestfit.models.diazenylium")
 
     class _NS:
         pass
     ns = _NS()
     ns.core, ns.hyperfine, ns.ammonia, ns.gaussian = core, hyperfine, ammonia, gaussian
+    ns.diazenylium = diazenylium
     _mods = ns
     return ns
 

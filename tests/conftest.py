@@ -37,3 +37,8 @@ def nb():
     build.build()
     import nestfit_b200
     return nestfit_b200
+
+
+@pytest.fixture(scope="session")
+def n2hp_golden():
+    return dict(np.load(GOLDEN / "n2hp_golden.npz"))

@@ -170,5 +170,45 @@ def main():
         print(f, (OUT / f).stat().st_size, "bytes")
 
 
+def make_n2hp():
+    """n2hp_golden.npz: N2H+ (diazenylium.pyx) spectra and lnL of the compiled reference for the
+    three transitions, ncomp 1..3, incl. an optically thick and a band-edge vector."""
+    dz = m.diazenylium
+    rng = np.random.default_rng(20261019)
+    out = {}
+    nus = [93173.7637e6, 186344.8420e6, 279511.8325e6]
+    nchan = 800
+    for t in (1, 2, 3):
+        x = ref.bench_axis(nus[t - 1], nchan=nchan, dv=0.06)
+        out[f"x{t}"] = x
+        for ncomp in (1, 2, 3):
+            NV = 6
+            P = np.concatenate([np.sort(rng.uniform(-6, 6, (NV, ncomp)), axis=1), rng.uniform(3, 25, (NV, ncomp)),
+                                rng.uniform(-1.5, 1.3, (NV, ncomp)), rng.uniform(0.07, 1.6, (NV, ncomp))], axis=1)
+            P[1, 2 * ncomp] = 1.8                # optically thick main component
+            P[2, 0] = 21.0                       # windows clipped at the band edge
+            s0 = dz.DiazenyliumSpectrum(x, np.zeros(nchan), 0.1, trans_id=t)
+            dz.nnhp_predict(s0, P[0].copy())
+            data = s0.get_spec() + rng.normal(0, 0.1, nchan)
+            sd = dz.DiazenyliumSpectrum(x, data.copy(), 0.1, trans_id=t)
+            pred = np.empty((NV, nchan))
+            lnL = np.empty(NV)
+            for b in range(NV):
+                dz.nnhp_predict(sd, P[b].copy())
+                pred[b] = sd.get_spec()
+                lnL[b] = sd.loglikelihood
+            out[f"params{t}_{ncomp}"] = P
+            out[f"data{t}_{ncomp}"] = data
+            out[f"pred{t}_{ncomp}"] = pred
+            out[f"lnL{t}_{ncomp}"] = lnL
+    # two transitions scored together through the reference's runner-style sum
+    np.savez_compressed(OUT / "n2hp_golden.npz", **out)
+    print("n2hp_golden.npz", (OUT / "n2hp_golden.npz").stat().st_size, "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-n2hp" in sys.argv:
+        make_n2hp()
+    else:
+        main()
+        make_n2hp()

@@ -145,3 +145,17 @@ def test_oracle_equals_compiled_reference():
                 m.ammonia.amm_predict(s, P[b].copy())
                 want = s.get_spec()
                 assert np.max(np.abs(out["pred"][b, t] - want)) <= 1e-11 * max(want.max(), 1e-30)
+
+
+@pytest.mark.parametrize("trans", [1, 2, 3])
+def test_n2hp_against_golden(n2hp_golden, trans):
+    """N2H+ (diazenylium.pyx:140-154) restatement against the compiled reference's fixtures."""
+    g = n2hp_golden
+    for ncomp in (1, 2, 3):
+        P = g[f"params{trans}_{ncomp}"]
+        o = orc.n2hp_batch([g[f"x{trans}"]], [trans], P, ncomp, data=g[f"data{trans}_{ncomp}"][None, None],
+                           noise=0.1, want_pred=True)
+        want = g[f"pred{trans}_{ncomp}"]
+        peak = np.abs(want).max(axis=1, keepdims=True)
+        assert (np.abs(o["pred"][:, 0] - want) <= 1e-12 * peak).all()
+        np.testing.assert_allclose(o["lnL"], g[f"lnL{trans}_{ncomp}"], rtol=1e-10, atol=1e-8)
