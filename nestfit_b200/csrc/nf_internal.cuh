@@ -77,6 +77,7 @@ struct NfLikeArgs {
     const int32_t *pix_of_vec;  // may be NULL
     int64_t vecs_per_pix;
     int64_t B;
+    const int32_t *B_dev;       // optional: device-resident vector count (<= B, which then only sizes the grid)
     int64_t pix_stride;         // floats per pixel = n_spec * n_pad
     double *lnL;                // may be NULL
     float *pred;                // may be NULL: [B][n_spec][n_chan]
@@ -103,7 +104,7 @@ cudaError_t nf_launch_pack_rows(const void *src, int src_f64, float *dst, int64_
                                 int n_chan, int n_pad, cudaStream_t st);
 // nf_priors.cu
 cudaError_t nf_launch_prior_transform(const nf_priors *pr, double *u, int64_t B, int ncomp,
-                                      cudaStream_t st);
+                                      cudaStream_t st, const int32_t *B_dev = nullptr);
 
 extern thread_local double g_nf_last_kernel_ms;
 extern thread_local int64_t g_nf_last_launches;

@@ -215,6 +215,9 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
 
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t b0 = (int64_t)blockIdx.x * tile;
+    // the vector count may live on the device (lock-step sampler): a.B then only sized the grid
+    const int64_t B = a.B_dev ? min(a.B, (int64_t)__ldg(a.B_dev)) : a.B;
+    if (b0 >= B) return;
     constexpr bool have_data = !WRITE_PRED;
     int64_t pix0 = 0;
     if (have_data) {
@@ -231,7 +234,7 @@ nf_like_kernel(const __grid_constant__ NfLikeArgs a)
     const int nchunks = (a.n_chan + 31) >> 5;
     const uint32_t sdata_addr = smem_u32(sdata) + (uint32_t)lane * 4u;
 
-    for (int64_t b = b0 + warp; b < b0 + tile && b < a.B; b += NF_WARPS_PER_CTA) {
+    for (int64_t b = b0 + warp; b < b0 + tile && b < B; b += NF_WARPS_PER_CTA) {
         const int64_t pbase = b * ndim;
         int64_t pix = 0;
         if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;

@@ -300,6 +300,9 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t b0 = (int64_t)blockIdx.x * tile;
+    // the vector count may live on the device (lock-step sampler): a.B then only sized the grid
+    const int64_t B = a.B_dev ? min(a.B, (int64_t)__ldg(a.B_dev)) : a.B;
+    if (b0 >= B) return;
     constexpr bool have_data = !WRITE_PRED;
     int64_t pix0 = 0;
     if (have_data) {
@@ -319,7 +322,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
     const int vb = min(32 / ipv, 8);
     int64_t bw_end = b0 + (int64_t)(warp + 1) * vpw;
     if (bw_end > b0 + tile) bw_end = b0 + tile;
-    if (bw_end > a.B) bw_end = a.B;
+    if (bw_end > B) bw_end = B;
 
     // FastExp's Taylor branch for 1 - exp(-tau), tau < 2^-5 (fastexp.c:265-270), in tp = -log2(e) tau
     const float kC1 = -(float)NF_LN2, kC2 = -(float)(0.5 * NF_LN2 * NF_LN2),

@@ -243,9 +243,11 @@ __device__ void prior_apply(const nf_prior_desc *pr, int k, const nf_dist_desc *
 }
 
 __global__ void nf_prior_transform_kernel(const nf_prior_desc *pr, int n_prior, const nf_dist_desc *dd,
-                                          const double *tables, double *u, int64_t B, int ndim, int ncomp)
+                                          const double *tables, double *u, int64_t B, int ndim, int ncomp,
+                                          const int32_t *B_dev)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B_dev) B = min(B, (int64_t)*B_dev);     // device-resident count; B only sized the grid
     if (b >= B) return;
     double *row = u + b * ndim;
     for (int k = 0; k < n_prior; ++k)
@@ -254,13 +256,14 @@ __global__ void nf_prior_transform_kernel(const nf_prior_desc *pr, int n_prior, 
 
 }  // namespace
 
-cudaError_t nf_launch_prior_transform(const nf_priors *pr, double *u, int64_t B, int ncomp, cudaStream_t st)
+cudaError_t nf_launch_prior_transform(const nf_priors *pr, double *u, int64_t B, int ncomp, cudaStream_t st,
+                                      const int32_t *B_dev)
 {
     if (B <= 0) return cudaSuccess;
     const int threads = 128;
     const int64_t grid = (B + threads - 1) / threads;
     nf_prior_transform_kernel<<<(unsigned)grid, threads, 0, st>>>(pr->priors, pr->n_prior, pr->dists, pr->tables,
-                                                                  u, B, pr->n_model * ncomp, ncomp);
+                                                                  u, B, pr->n_model * ncomp, ncomp, B_dev);
     return cudaGetLastError();
 }
 

@@ -168,12 +168,14 @@ __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32
 
 // ---- bounding ellipsoid of the live set (one CTA per active run) -----------
 __global__ void __launch_bounds__(128)
-ns_bounds_kernel(const int32_t *act, const int32_t *nlive_arr, const int32_t *it_arr, const double *live_u,
-                 double *bound, int nlive_max, int ndim, double efr, const int32_t *mode, const int32_t *coh_step)
+ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nlive_arr, const int32_t *it_arr,
+                 const double *live_u, double *bound, int nlive_max, int ndim, double efr, const int32_t *mode,
+                 const int32_t *coh_step)
 {
     __shared__ double s_mean[NS_MAX_DIM];
     __shared__ double s_c[NS_MAX_DIM][NS_MAX_DIM + 1];
     __shared__ double s_red[128];
+    if ((int)blockIdx.x >= *n_act_dev) return;
     const int r = act[blockIdx.x];
     // a random-walk cohort keeps the metric it started with: rebuild only at cohort start
     if (mode[r] == 1 && coh_step[r] != 0) return;
@@ -266,7 +268,7 @@ ns_bounds_kernel(const int32_t *act, const int32_t *nlive_arr, const int32_t *it
 // Device-side view of the sampler state handed to the kernels by value.
 struct NsDev {
     const int32_t *act;
-    int n_act;
+    const int32_t *n_act_dev;          // {n_act, n_cand}: grids are sized from a host-side upper bound
     const int32_t *pix_ids, *nlive;
     double *live_u, *live_th, *live_l;
     double *cand_u, *cand_th, *cand_l;
@@ -305,6 +307,7 @@ __device__ void unit_ball(Philox &rng, int d, double *y)
 __global__ void ns_propose_kernel(const NsDev D)
 {
     const int a = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
+    if (a >= *D.n_act_dev) return;
     const int r = D.act[a];
     if (k >= D.krun[r]) return;
     const int64_t idx = (int64_t)D.cand_off[a] + k;
@@ -313,7 +316,7 @@ __global__ void ns_propose_kernel(const NsDev D)
     Philox rng(D.seed, (uint32_t)r, (uint32_t)D.lock, (uint32_t)k);
     double u[NS_MAX_DIM], y[NS_MAX_DIM];
     bool ok = false;
-    if (D.mode[r] == 0) {
+    if (D.mode[r] != 1) {
         // rejection sampling from the bounding ellipsoid (or the unit cube itself)
         if (B[d + d * d] > 0.5) {
             for (int j = 0; j < d; ++j) u[j] = rng.uniform();
@@ -392,10 +395,9 @@ __device__ __forceinline__ void warp_argmin(const double *LL, int nl, int lane, 
 // point, that point dies with prior-mass weight X_{i-1} - X_i and the candidate takes
 // its slot.  Warp-cooperative; returns true when the candidate was inserted.
 __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshell, const double *cu,
-                           const double *ct, double lc, RunState &S)
+                           const double *ct, double lc, RunState &S, double *LL)
 {
     const int d = D.d;
-    double *LL = D.live_l + (int64_t)r * D.nlive_max;
     double mn;
     int im;
     warp_argmin(LL, nl, lane, mn, im);
@@ -421,7 +423,7 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
     }
     double *lu = D.live_u + ((int64_t)r * D.nlive_max + im) * d, *lt = D.live_th + ((int64_t)r * D.nlive_max + im) * d;
     for (int j = lane; j < d; j += 32) { lu[j] = cu[j]; lt[j] = ct[j]; }
-    if (lane == 0) LL[im] = lc;
+    if (lane == 0) { LL[im] = lc; D.live_l[(int64_t)r * D.nlive_max + im] = lc; }
     __syncwarp();
     ++S.it;
     S.lmax = fmax(S.lmax, lc);
@@ -435,10 +437,14 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
 // ---- consume the scored proposals (one warp per active run) ------------------
 __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
 {
+    extern __shared__ double s_live_l[];     // [warps per CTA][nlive_max]: this run's live log-likelihoods
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= D.n_act) return;
+    if (w >= *D.n_act_dev) return;
     const int r = D.act[w];
     const int nl = D.nlive[r], d = D.d, K = D.krun[r], KS = D.Kmax;
+    double *LL = s_live_l + (size_t)(threadIdx.x >> 5) * D.nlive_max;
+    for (int p = lane; p < nl; p += 32) LL[p] = D.live_l[(int64_t)r * D.nlive_max + p];
+    __syncwarp();
     RunState S;
     S.lnZ = D.lnZ[r]; S.H = D.H[r]; S.lmax = D.lmax[r]; S.it = D.it[r]; S.nd = D.n_dead[r]; S.done = false;
     int64_t nev = D.n_eval[r];
@@ -446,19 +452,26 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     const double lnshell = log(-expm1(-1.0 / (double)nl));
     const int64_t c0 = (int64_t)D.cand_off[w];  // candidate slots of this run in this iteration
     int mode = D.mode[r];
-    if (mode == 0) {
+    // random-walk cohorts of all runs start on the same lock-steps (multiples of `walks`), so that
+    // the serial insertion work at a cohort's end falls on one lock-step in `walks` for every run
+    if (mode == 2 && (D.lock + 1) % D.walks == 0) {
+        mode = 1;
+        if (lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
+    }
+    if (mode != 1) {
         int n_ok = 0, n_acc = 0;
         for (int k = 0; k < K && !S.done; ++k) {
             const double *cu = D.cand_u + (c0 + k) * d;
             if (cu[0] == cu[0]) { ++nev; ++n_ok; }
-            if (try_insert(D, r, nl, lane, lnshell, cu, D.cand_th + (c0 + k) * d, D.cand_l[c0 + k], S)) ++n_acc;
+            if (try_insert(D, r, nl, lane, lnshell, cu, D.cand_th + (c0 + k) * d, D.cand_l[c0 + k], S, LL)) ++n_acc;
         }
         // windowed acceptance rate; fall back to the random walk when rejection sampling stalls
         int ea = D.eff_acc[r] + n_acc, ep = D.eff_prop[r] + n_ok;
         if (ep >= 512) {
-            if (!(D.flags & 2) && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
-                mode = 1;
-                if (lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
+            if (!(D.flags & 2) && mode == 0 && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
+                mode = 2;                      // hand over to the random walk at the next aligned lock-step
+                if (lane == 0) D.mode[r] = 2;
+                if ((D.lock + 1) % D.walks == 0 && lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
             }
             ea = 0; ep = 0;
         }
@@ -468,7 +481,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
         double lstar;
         if (step == 0) {                        // a new cohort: threshold = current worst live point
             int im;
-            warp_argmin(D.live_l + (int64_t)r * D.nlive_max, nl, lane, lstar, im);
+            warp_argmin(LL, nl, lane, lstar, im);
             if (lane == 0) { D.lstar[r] = lstar; D.coh_acc[r] = 0; }
         } else {
             lstar = D.lstar[r];
@@ -502,7 +515,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
             for (int k = 0; k < K && !S.done; ++k) {
                 if (!D.chain_moved[(int64_t)r * KS + k]) continue;      // never moved: still a live point
                 try_insert(D, r, nl, lane, lnshell, D.chain_u + ((int64_t)r * KS + k) * d,
-                           D.chain_th + ((int64_t)r * KS + k) * d, D.chain_l[(int64_t)r * KS + k], S);
+                           D.chain_th + ((int64_t)r * KS + k) * d, D.chain_l[(int64_t)r * KS + k], S, LL);
             }
             // step size follows the acceptance fraction (target 1/2)
             const double facc = (double)cacc / (double)(K * D.walks);
@@ -567,7 +580,7 @@ ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t
         int k = 0;
         if (a < n_act) {
             const int r = act[a];
-            if (mode[r] == 0 || coh_step[r] == 0) krun[r] = knew;
+            if (mode[r] != 1 || coh_step[r] == 0) krun[r] = knew;
             k = krun[r];
         }
         s_cnt[tid] = k;
@@ -583,7 +596,7 @@ ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t
         if (tid == 1023) s_base += s_cnt[1023];
         __syncthreads();
     }
-    if (tid == 0) { *n_act_dev = n_act; n_act_host[0] = n_act; n_act_host[1] = s_base; }
+    if (tid == 0) { n_act_dev[0] = n_act; n_act_dev[1] = s_base; n_act_host[0] = n_act; n_act_host[1] = s_base; }
 }
 
 // ---- finalisation: add the live points, normalise, pick best-fit / MAP ------
@@ -648,17 +661,18 @@ ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double
 
 #define NS_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
-int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_t B, double *lnl)
+int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_t B, double *lnl,
+          const int32_t *B_dev = nullptr)
 {
-    NS_CUDA(nf_launch_prior_transform(s->pr, params, B, s->ncomp, s->stream));
+    NS_CUDA(nf_launch_prior_transform(s->pr, params, B, s->ncomp, s->stream, B_dev));
     NfLikeArgs a;
     std::memset(&a, 0, sizeof(a));
     const nf_pixels *px = s->px;
     a.data = px->data; a.inv2s2 = px->inv2s2; a.params = params; a.pix_of_vec = pix; a.vecs_per_pix = 1;
-    a.B = B; a.pix_stride = (int64_t)px->n_spec * px->n_pad; a.lnL = lnl; a.pred = nullptr; a.param_f64 = 1;
+    a.B = B; a.B_dev = B_dev; a.pix_stride = (int64_t)px->n_spec * px->n_pad; a.lnL = lnl; a.pred = nullptr; a.param_f64 = 1;
     a.ncomp = s->ncomp; a.n_spec = px->n_spec; a.n_chan = px->n_chan; a.n_pad = px->n_pad;
     a.cold = (s->flags & NF_FLAG_COLD) != 0; a.lte = (s->flags & NF_FLAG_LTE) != 0;
-    a.tile_vecs = (int)(vpp > 0 ? vpp : 0);     // one CTA tile = the proposals of one run (one pixel)
+    a.tile_vecs = (int)(vpp > 0 ? vpp : 0);     // a CTA tile never straddles the proposals of two runs (pixels)
     for (int k = 0; k < px->n_spec; ++k) {
         a.spec[k] = px->spec[k];
         if (px->spec[k].para) a.need_para = 1; else a.need_ortho = 1;
@@ -720,7 +734,7 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
     A(dalloc(&s->n_dead, R)); A(dalloc(&s->it, R)); A(dalloc(&s->done, R)); A(dalloc(&s->n_eval, R));
     A(dalloc(&s->bestfit, R * D)); A(dalloc(&s->mapfit, R * D));
-    A(dalloc(&s->act, R)); A(dalloc(&s->n_act_dev, 1));
+    A(dalloc(&s->act, R)); A(dalloc(&s->n_act_dev, 2));
     A(dalloc(&s->mode, R)); A(dalloc(&s->coh_step, R)); A(dalloc(&s->coh_acc, R)); A(dalloc(&s->eff_acc, R));
     A(dalloc(&s->eff_prop, R)); A(dalloc(&s->chain_moved, R * K)); A(dalloc(&s->lstar, R)); A(dalloc(&s->scale, R));
     A(dalloc(&s->chain_u, R * K * D)); A(dalloc(&s->chain_th, R * K * D)); A(dalloc(&s->chain_l, R * K));
@@ -799,13 +813,27 @@ int nf_ns_run(nf_sampler *s)
         if (e != cudaSuccess) rc = (int)e;
     }
     int n_act = rc == NF_OK ? s->n_act_host[0] : 0;
-    int64_t n_cand = rc == NF_OK ? s->n_act_host[1] : 0;
     int lock = 0;
+    // The counts of the next lock-step (active runs, candidates) stay on the device; the host
+    // sizes grids from upper bounds -- the active list only shrinks and the candidate total is
+    // at most n_act K + target -- and reads the counts back every `sync_every` lock-steps.
+    const size_t upd_smem = (size_t)4 * NL * sizeof(double);
+    if (cudaFuncSetAttribute(ns_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem) != cudaSuccess)
+        rc = NF_EINVAL;
+    const bool debug = getenv("NF_NS_DEBUG") != nullptr;
+    // NF_NS_PROFILE=1: per-kernel device time of every lock-step (CUDA events, synchronous)
+    const bool prof = getenv("NF_NS_PROFILE") != nullptr;
+    cudaEvent_t pev[6];
+    double pms[5] = {0, 0, 0, 0, 0}, ptail[5] = {0, 0, 0, 0, 0};
+    int ntail = 0;
+    double pwall = 0.0;
+    if (prof) for (int i = 0; i < 6; ++i) cudaEventCreate(&pev[i]);
+    const int sync_every = (debug || prof) ? 1 : 8;
     // lock-step iterations are bounded: a run needs at most max_iter * walks of them
     const int64_t lock_cap = (int64_t)s->cfg.max_iter * (int64_t)(s->walks + 1);
     while (rc == NF_OK && n_act > 0 && (int64_t)lock < lock_cap && lock < 2000000000) {
         NsDev D;
-        D.act = s->act; D.n_act = n_act; D.pix_ids = s->pix_ids; D.nlive = s->nlive;
+        D.act = s->act; D.n_act_dev = s->n_act_dev; D.pix_ids = s->pix_ids; D.nlive = s->nlive;
         D.live_u = s->live_u; D.live_th = s->live_th; D.live_l = s->live_l;
         D.cand_u = s->cand_u; D.cand_th = s->cand_th; D.cand_l = s->cand_l; D.cand_pix = s->cand_pix;
         D.bound = s->bound; D.dead_th = s->dead_th; D.dead_l = s->dead_l; D.dead_lw = s->dead_lw;
@@ -817,21 +845,46 @@ int nf_ns_run(nf_sampler *s)
         D.K = K; D.Kmax = s->Kmax; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
         D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
         D.lock = lock;
-        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->nlive, s->it, s->live_u, s->bound, NL, d, s->cfg.efr,
-                                                s->mode, s->coh_step);
-        if (n_cand > s->cand_cap) { rc = NF_EINVAL; break; }     // cannot happen (see cand_cap)
+        int64_t cand_ub = (int64_t)n_act * K + (s->Kmax > K ? (int64_t)s->cfg.target_batch : 0);
+        if (cand_ub > s->cand_cap) cand_ub = s->cand_cap;
+        if (prof) cudaEventRecord(pev[0], st);
+        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->n_act_dev, s->nlive, s->it, s->live_u, s->bound, NL, d,
+                                                s->cfg.efr, s->mode, s->coh_step);
+        if (prof) cudaEventRecord(pev[1], st);
         ns_propose_kernel<<<dim3((unsigned)((s->Kmax + 127) / 128), (unsigned)n_act), 128, 0, st>>>(D);
-        rc = score(s, s->cand_th, s->cand_pix, K, n_cand, s->cand_l);
+        if (prof) cudaEventRecord(pev[2], st);
+        // few vectors in flight (tail of a wave): smaller CTA tiles, so that the launch spreads over
+        // more SMs and a lock-step's latency drops
+        const int tile = ((int64_t)n_act * K >= 32768 || K % 8 != 0) ? K : 8;
+        rc = score(s, s->cand_th, s->cand_pix, tile, cand_ub, s->cand_l, s->n_act_dev + 1);
         if (rc != NF_OK) break;
-        ns_update_kernel<<<(n_act * 32 + 127) / 128, 128, 0, st>>>(D);
+        if (prof) cudaEventRecord(pev[3], st);
+        ns_update_kernel<<<(n_act * 32 + 127) / 128, 128, upd_smem, st>>>(D);
+        if (prof) cudaEventRecord(pev[4], st);
         ns_compact_kernel<<<1, 1024, 0, st>>>(s->done, s->act, s->n_act_dev, s->n_act_host, R, s->mode, s->coh_step,
                                               s->krun, s->cand_off, K, s->Kmax, (int64_t)s->cfg.target_batch);
+        if (prof) {
+            cudaEventRecord(pev[5], st);
+            cudaEventSynchronize(pev[5]);
+            const bool tail = s->n_act_host[0] * K < 8192;
+            if (tail) ++ntail;
+            for (int i = 0; i < 5; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, pev[i], pev[i + 1]);
+                pms[i] += ms;
+                if (tail) ptail[i] += ms;
+            }
+            float ms = 0.f; cudaEventElapsedTime(&ms, pev[0], pev[5]); pwall += ms;
+            if (lock % 500 == 0)
+                fprintf(stderr, "[ns-prof] lock %d n_act %d n_cand %d\n", lock, s->n_act_host[0], s->n_act_host[1]);
+        }
         s->launches += 4;
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { rc = (int)e; break; }
-        n_act = s->n_act_host[0];
-        n_cand = s->n_act_host[1];
         ++lock;
+        if (lock % sync_every == 0) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = (int)e; break; }
+            n_act = s->n_act_host[0];
+        }
         if (getenv("NF_NS_DEBUG") && (lock % atoi(getenv("NF_NS_DEBUG"))) == 0 && n_act > 0) {
             // diagnostics of the first still-active run
             int32_t r0 = 0, it0 = 0; int64_t ne = 0; double z0 = 0, lm = 0;
@@ -863,6 +916,14 @@ int nf_ns_run(nf_sampler *s)
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = (int)e;
         s->launches += 1;
+    }
+    if (prof) {
+        fprintf(stderr, "[ns-prof] ncomp %d runs %lld lock-steps %d: bounds %.1f ms, propose %.1f, transform+likelihood %.1f, "
+                        "update %.1f, compact %.1f; sum of steps %.1f ms\n", s->ncomp, (long long)R, lock, pms[0], pms[1],
+                pms[2], pms[3], pms[4], pwall);
+        fprintf(stderr, "[ns-prof]   of which %d tail steps (n_act K < 8192): bounds %.1f ms, propose %.1f, transform+likelihood %.1f, "
+                        "update %.1f, compact %.1f\n", ntail, ptail[0], ptail[1], ptail[2], ptail[3], ptail[4]);
+        for (int i = 0; i < 6; ++i) cudaEventDestroy(pev[i]);
     }
     s->lock_iters = lock;
     if (prev >= 0) cudaSetDevice(prev);

@@ -208,11 +208,11 @@ class CubeFitter:
 
     def __init__(self, stack, utrans, runner_cls, runner_kwargs=None, lnZ_thresh=11, ncomp_max=2, mn_kwargs=None,
                  nlive_snr_fact=5, n_prop=32, max_pixels_per_wave=16384, seed=1234, store_posteriors=True,
-                 n_streams=4, min_pixels_per_stream=256):
+                 n_streams=1, pixels_per_stream=1024):
         """Same arguments as the reference (main.py:388-421) plus the batching knobs
         `n_prop` (proposals per pixel per lock-step iteration), `max_pixels_per_wave`
-        (pixels in flight per device wave), `n_streams` (sub-blocks of a wave that escalate
-        concurrently, each at least `min_pixels_per_stream` pixels) and `seed`."""
+        (pixels in flight per device wave), `n_streams` (host threads / CUDA streams that
+        escalate sub-blocks of `pixels_per_stream` pixels concurrently) and `seed`."""
         self.stack = stack
         self.utrans = utrans
         self.runner_cls = runner_cls
@@ -226,7 +226,7 @@ class CubeFitter:
         self.n_prop = n_prop
         self.max_pixels_per_wave = max_pixels_per_wave
         self.n_streams = n_streams
-        self.min_pixels_per_stream = min_pixels_per_stream
+        self.pixels_per_stream = pixels_per_stream
         self.seed = seed
         self.store_posteriors = store_posteriors
         self.stats = {}
@@ -312,23 +312,30 @@ class CubeFitter:
                     nbest[active[improved]] = ncomp
                     active = active[improved]
 
-            # Sub-blocks of the wave escalate independently on their own streams (one host thread
-            # each; the sampler call releases the GIL), so that the thin tail of one sub-block's
-            # run overlaps the bulk of another's instead of idling the GPU.
-            n_sub = max(1, min(self.n_streams, vidx.size // max(1, self.min_pixels_per_stream)))
+            # Sub-blocks of the wave escalate independently, each on its own stream, picked from a
+            # queue by `n_streams` host threads (the sampler call releases the GIL).  The workers
+            # drift apart, so the thin tail of one sub-block's run overlaps the bulk of another's
+            # instead of idling the GPU.
+            n_sub = max(1, vidx.size // max(1, self.pixels_per_stream)) if self.n_streams > 1 else 1
             subs = np.array_split(np.arange(vidx.size), n_sub)
             if n_sub == 1:
                 fit_sub(subs[0], 0)
             else:
                 errors = []
+                todo = list(enumerate(subs))[::-1]
 
-                def guarded(sub, tag):
-                    try:
-                        fit_sub(sub, tag)
-                    except BaseException as exc:   # re-raised in the caller's thread
-                        errors.append(exc)
+                def worker():
+                    while True:
+                        with lock:
+                            if not todo or errors:
+                                return
+                            tag, sub = todo.pop()
+                        try:
+                            fit_sub(sub, tag)
+                        except BaseException as exc:   # re-raised in the caller's thread
+                            errors.append(exc)
 
-                threads = [threading.Thread(target=guarded, args=(sub, t)) for t, sub in enumerate(subs)]
+                threads = [threading.Thread(target=worker) for _ in range(min(self.n_streams, n_sub))]
                 for th in threads:
                     th.start()
                 for th in threads:

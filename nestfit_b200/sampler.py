@@ -42,7 +42,7 @@ class NestedSamplingBatch:
         constrained random walk once its acceptance stalls; 'ellipsoid' / 'rwalk' force one.
         walks: random-walk steps per new point (0 = 20 + ndim).
         n_prop_max / target_batch: once few runs are still active each gets up to n_prop_max
-        proposals per lock-step (default 4 n_prop) so that a launch keeps ~target_batch vectors."""
+        proposals per lock-step (default 16 n_prop) so that a launch keeps ~target_batch vectors."""
         lib = _lib.load()
         self.block, self.utrans, self.ncomp = block, utrans, int(ncomp)
         if pix_ids is None:
@@ -60,7 +60,7 @@ class NestedSamplingBatch:
                             max_samples=int(max_samples), bound_update_interval=int(walks),
                             flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method], tol=float(tol),
                             efr=float(efr), seed=int(seed),
-                            n_prop_max=int(4 * n_prop if n_prop_max is None else n_prop_max),
+                            n_prop_max=int(16 * n_prop if n_prop_max is None else n_prop_max),
                             target_batch=int(target_batch))
         flags = (_lib.NF_FLAG_COLD if cold else 0) | (_lib.NF_FLAG_LTE if lte else 0)
         out = C.c_void_p()

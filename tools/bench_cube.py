@@ -11,7 +11,8 @@ ap.add_argument('--size', type=int, default=64)
 ap.add_argument('--ncomp-max', type=int, default=3)
 ap.add_argument('--nprop', type=int, default=32)
 ap.add_argument('--chan', type=int, default=1000)
-ap.add_argument('--streams', type=int, default=4)
+ap.add_argument('--streams', type=int, default=1)
+ap.add_argument('--pps', type=int, default=1024)
 args = ap.parse_args()
 ut = nb.get_irdc_priors()
 n = args.size
@@ -22,7 +23,7 @@ stack = make_synth_stack((n, n), ut, ncomp_map=ncomp_map, n_chan=args.chan, dv=0
 t_build = time.perf_counter() - t0
 fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=args.ncomp_max, lnZ_thresh=11,
                        mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=args.nprop,
-                       max_pixels_per_wave=16384, n_streams=args.streams)
+                       max_pixels_per_wave=16384, n_streams=args.streams, pixels_per_stream=args.pps)
 idx = nb.get_block_indices((n, n), 1)[0]
 res = fitter.fit_block(idx, device=0, verbose=False)
 nb_map = res['nbest'].reshape(n, n)
