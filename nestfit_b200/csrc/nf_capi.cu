@@ -117,6 +117,7 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
         (e = cudaMalloc(&px->data, nrow * px->n_pad * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&px->inv2s2, nrow * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&px->null_lnz, (size_t)n_pix * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&px->d2chunk, nrow * (px->n_pad / 32) * sizeof(float))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&px->streams[0], cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&px->streams[1], cudaStreamNonBlocking)) != cudaSuccess) {
         nf_pixels_free(px);
@@ -142,6 +143,7 @@ int finish_pixels(nf_pixels *px)
 {
     NF_CUDA(nf_launch_null_lnz(px->data, px->inv2s2, px->null_lnz, px->n_pix, px->n_spec, px->n_chan,
                                px->n_pad, 0));
+    NF_CUDA(nf_launch_d2chunk(px->data, px->d2chunk, px->n_pix * px->n_spec, px->n_pad, 0));
     NF_CUDA(cudaDeviceSynchronize());
     return NF_OK;
 }
@@ -173,6 +175,7 @@ int make_args(const nf_pixels *px, const void *params, int param_dtype, const in
     std::memset(a, 0, sizeof(*a));
     a->data = use_data ? px->data : nullptr;
     a->inv2s2 = px->inv2s2;
+    a->d2chunk = use_data ? px->d2chunk : nullptr;
     a->params = params;
     a->pix_of_vec = use_data ? pix_of_vec : nullptr;
     a->vecs_per_pix = vecs_per_pix > 0 ? vecs_per_pix : 1;
@@ -268,6 +271,7 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
             // implicit pixel map continues across chunks: shift by whole pixels
             a.data = px->data + (b0 / a.vecs_per_pix) * a.pix_stride;
             a.inv2s2 = px->inv2s2 + (b0 / a.vecs_per_pix) * px->n_spec;
+            a.d2chunk = px->d2chunk + (b0 / a.vecs_per_pix) * px->n_spec * (px->n_pad / 32);
         }
         NF_CUDA(cudaEventRecord(ev0[slot], st));
         cudaError_t e = launch_model(model, a, st);
@@ -400,6 +404,7 @@ int nf_pixels_free(nf_pixels *px)
     if (px->data) cudaFree(px->data);
     if (px->inv2s2) cudaFree(px->inv2s2);
     if (px->null_lnz) cudaFree(px->null_lnz);
+    if (px->d2chunk) cudaFree(px->d2chunk);
     for (int i = 0; i < 2; ++i) {
         if (px->stage_dev[i]) cudaFree(px->stage_dev[i]);
         if (px->streams[i]) cudaStreamDestroy(px->streams[i]);

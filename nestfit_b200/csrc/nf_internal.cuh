@@ -50,6 +50,7 @@ struct nf_pixels {
     float *data;                    // [n_pix][n_spec][n_pad]
     double *inv2s2;                 // [n_pix][n_spec]  1/(2 sigma^2)
     double *null_lnz;               // [n_pix]
+    float *d2chunk;                 // [n_pix][n_spec][n_pad/32]  sum of d^2 over each 32-channel chunk
     NfSpecMeta spec[NF_MAX_SPEC];
     // pipelined host-call resources
     cudaStream_t streams[2];
@@ -73,6 +74,7 @@ struct nf_priors {
 struct NfLikeArgs {
     const float *data;          // may be NULL (predict only)
     const double *inv2s2;
+    const float *d2chunk;       // per pixel, spectrum and 32-channel chunk: sum of d^2 (chunks no line touches)
     const void *params;
     const int32_t *pix_of_vec;  // may be NULL
     int64_t vecs_per_pix;
@@ -100,6 +102,7 @@ cudaError_t nf_model_init_device_tables(int device);
 cudaError_t nf_launch_null_lnz(const float *data, const double *inv2s2, double *out,
                                int64_t n_pix, int n_spec, int n_chan, int n_pad,
                                cudaStream_t st);
+cudaError_t nf_launch_d2chunk(const float *data, float *out, int64_t n_rows, int n_pad, cudaStream_t st);
 cudaError_t nf_launch_pack_rows(const void *src, int src_f64, float *dst, int64_t rows,
                                 int n_chan, int n_pad, cudaStream_t st);
 // nf_priors.cu

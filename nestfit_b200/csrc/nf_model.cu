@@ -641,6 +641,26 @@ cudaError_t nf_launch_null_lnz(const float *data, const double *inv2s2, double *
     return cudaGetLastError();
 }
 
+// sum of d^2 over every 32-channel chunk of every (pixel, spectrum) row: one warp per chunk
+__global__ void nf_d2chunk_kernel(const float *data, float *out, int64_t n_chunks_total)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_chunks_total) return;
+    const float d = data[g * 32 + lane];
+    const float v = warp_sum_f32(d * d);
+    if (lane == 0) out[g] = v;
+}
+
+cudaError_t nf_launch_d2chunk(const float *data, float *out, int64_t n_rows, int n_pad, cudaStream_t st)
+{
+    const int64_t total = n_rows * (n_pad / 32);
+    if (total <= 0) return cudaSuccess;
+    const int wpb = 8;
+    nf_d2chunk_kernel<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(data, out, total);
+    return cudaGetLastError();
+}
+
 // rows of n_chan (f32 or f64) -> zero-padded FP32 rows of n_pad
 template <typename T>
 __global__ void nf_pack_rows_kernel(const T *src, float *dst, int64_t rows, int n_chan, int n_pad)

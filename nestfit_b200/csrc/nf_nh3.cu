@@ -118,8 +118,10 @@ struct __align__(16) Nh3Pair {
 // transitions in use) followed by this fixed part.
 template <int NC>
 struct __align__(16) Nh3Scratch {
-    uint4 tab[36];                        // per chunk and component: smem address of the first pair | pairs << 18;
-                                          // doubles as the counting array cnt[NC][36] while the table is built
+    uint4 seg[32 * NC];                   // work list of a super-block, one record per (chunk, component) that has
+                                          // lines: {first pair smem address | pairs << 18, amplitude smem address,
+                                          // data byte offset of the chunk | last-of-chunk << 31, float(32 chunk)};
+                                          // doubles as the counting array cnt[NC][36] while the list is built
     float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
     double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
     float tauL[32];                       // log2(log2(e) * tau_main)
@@ -250,6 +252,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float2 lds64(uint32_t addr)
 {
     float2 v;
@@ -295,7 +303,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
     float *pairf = reinterpret_cast<float *>(wbase);
     short2 *keys = reinterpret_cast<short2 *>(wbase + pair_bytes);   // per line: first chunk, first chunk after its window
     Scratch &sc = *reinterpret_cast<Scratch *>(wbase + pair_bytes + key_bytes);
-    uint32_t *cw = reinterpret_cast<uint32_t *>(sc.tab);   // cnt[c][g] = cw[c * 36 + g]
+    uint32_t *cw = reinterpret_cast<uint32_t *>(sc.seg);   // cnt[c][g] = cw[c * 36 + g]
     const uint32_t pair_addr = smem_u32(pairf);
 
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
@@ -317,6 +325,10 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
     const int n_spec = a.n_spec;
     const int ipv = NC * n_spec;
     const int nchunks = (a.n_chan + 31) >> 5;
+    float lane_f;                 // kept in registers (volatile asm: never rematerialised inside the main loop)
+    uint32_t lane4;
+    asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(lane_f) : "r"(lane));
+    asm volatile("shl.b32 %0, %1, 2;" : "=r"(lane4) : "r"(lane));
     // the warp's vectors: a contiguous slice of the tile, set up in batches of vb
     const int vpw = (tile + NH3_WARPS - 1) / NH3_WARPS;
     const int vb = min(32 / ipv, 8);
@@ -390,7 +402,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                             hh = 0.5f * (float)(hi - 1 - lo);
                         }
                         if (act) {
-                            keys[c * nkey + i] = make_short2((short)kE, (short)kF);
+                            if (nkey) keys[c * nkey + i] = make_short2((short)kE, (short)kF);
                             atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u);          // table counts of super-block 0
                             atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x10000u);
                             // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
@@ -414,13 +426,17 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                 // amplitude lines of this spectrum: one float4 {intercept_L, intercept_R, slope_L, slope_R} per component
                 const uint32_t amp_addr = smem_u32(&sc.amp[k * ipv + s]);
                 // this pixel's row: the CTA's staged copy in shared memory when the vector belongs to
-                // the tile's pixel, else straight from HBM/L2 (generic pointer, one LD per chunk)
-                const float *drow = nullptr;
-                if (have_data)
-                    drow = (pix == pix0 ? sdata + s * a.n_pad : a.data + pix * a.pix_stride + (int64_t)s * a.n_pad) + lane;
+                // the tile's pixel, else straight from HBM/L2
+                const bool staged = have_data && pix == pix0;
+                const uint32_t srow = staged ? smem_u32(sdata + s * a.n_pad) : 0u;   // 128-byte aligned
+                const char *grow = nullptr;
+                if (have_data) grow = reinterpret_cast<const char *>(a.data + pix * a.pix_stride + (int64_t)s * a.n_pad);
+                if (WRITE_PRED)       // chunks without lines stay zero; the others are overwritten by the same lane
+                    for (int j = lane; j < a.n_chan; j += 32) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
                 float acc = 0.0f;
                 for (int sb = 0; sb < nchunks; sb += 32) {
-                    // ---- T: per-chunk dispatch table, lanes <-> chunks ----
+                    // ---- T: work list of the super-block, lanes <-> chunks ----
+                    int nseg;
                     {
                         if (sb > 0) {   // later super-blocks (n_chan > 1024): recount from the stored keys
                             for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
@@ -445,7 +461,8 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 #pragma unroll
                         for (int c = 0; c < NC; ++c) v[c] = cw[c * 36 + lane];
                         __syncwarp();
-                        uint32_t ent[4] = {0u, 0u, 0u, 0u};
+                        uint32_t ent[NC];
+                        int n_mine = 0;
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
 #pragma unroll
@@ -453,63 +470,80 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                                 const uint32_t u = __shfl_up_sync(NF_FULL, v[c], o);
                                 if (lane >= o) v[c] += u;
                             }
+                            // the lines touching chunk g are the run [#ended(g), #started(g)) of the sorted records
                             const int end = (int)(v[c] & 0xffffu), first = (int)(v[c] >> 16);
                             const int cnt = end - first;
                             const uint32_t addr = pair_addr + (uint32_t)(((c * 2 + (first & 1)) * npair + (first >> 1)) * (int)sizeof(Nh3Pair));
                             ent[c] = cnt > 0 ? (addr | ((uint32_t)((cnt + 1) >> 1) << 18)) : 0u;
+                            n_mine += cnt > 0;
                         }
-                        sc.tab[lane] = make_uint4(ent[0], ent[1], ent[2], ent[3]);
-                        __syncwarp();
-                    }
-                    // ---- M: main loop over the chunks of this super-block ----
-                    const int cend = min(32, nchunks - sb);
-                    float xj = (float)((sb << 5) + lane);
-                    const float *dp = have_data ? drow + (sb << 5) : nullptr;
-                    const uint4 *tp = sc.tab;
-                    for (int cc = 0; cc < cend; ++cc, xj += 32.0f, dp += 32, ++tp) {
-                        const uint4 e4 = *tp;
-                        const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
-                        float d = 0.0f;
-                        if (have_data) d = *dp;
-                        if ((e4.x | e4.y | e4.z | e4.w) == 0u) {   // no line of any component touches this chunk
-                            if (WRITE_PRED) {
-                                const int j = ((sb + cc) << 5) + lane;
-                                if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
-                            }
-                            acc = fmaf(d, d, acc);
-                            continue;
+                        int incl = n_mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int u = __shfl_up_sync(NF_FULL, incl, o);
+                            if (lane >= o) incl += u;
                         }
-                        const uint64_t xj2 = pack2(xj, xj);
-                        float m = 0.0f;
+                        nseg = __shfl_sync(NF_FULL, incl, 31);
+                        int at = incl - n_mine;
+                        const int g = sb + lane;
+                        const uint32_t xbits = __float_as_uint((float)(g << 5));
+                        int left = n_mine;
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
-                            const uint32_t ec = ent[c];
-                            if (ec == 0u) continue;
-                            uint32_t ra = ec & 0x3ffffu;
-                            const uint32_t rend = ra + (ec >> 18) * (uint32_t)sizeof(Nh3Pair);
-                            float tpv = 0.0f;                            // -log2(e) * tau_j
-                            // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
-                            // whose own window test masks it off in this chunk
+                            if (ent[c] != 0u) {
+                                --left;
+                                sc.seg[at++] = make_uint4(ent[c], amp_addr + (uint32_t)(c * n_spec) * 16u,
+                                                          (srow + ((uint32_t)g << 7)) | (left == 0 ? 0x80000000u : 0u), xbits);
+                            }
+                        }
+                        // a chunk no line touches contributes its sum of d^2 (kept per pixel in HBM)
+                        if (have_data && n_mine == 0 && g < nchunks)
+                            acc += __ldg(a.d2chunk + (pix * n_spec + s) * (int64_t)(a.n_pad >> 5) + g);
+                        __syncwarp();
+                    }
+                    // ---- M: main loop over the (chunk, component) records of this super-block ----
+                    uint32_t sa = smem_u32(sc.seg);
+                    const uint32_t send = sa + (uint32_t)nseg * 16u;
+                    float m = 0.0f;
 #pragma unroll 1
-                            do {
-                                nh3_pair_term(tpv, ra, xj2);
-                                ra += (uint32_t)sizeof(Nh3Pair);
-                            } while (ra != rend);
-                            // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
-                            const float e1s = tpv * fmaf(tpv, fmaf(tpv, kC3, kC2), kC1);
-                            const float e1l = 1.0f - ex2_approx(tpv);
-                            const float e1 = tpv > kThr ? e1s : e1l;
-                            float aL, aR;
-                            const float4 am = lds128(amp_addr + (uint32_t)(c * n_spec) * 16u);   // {i_L, i_R, s_L, s_R}
-                            unpack2(fma2(pack2(am.z, am.w), xj2, pack2(am.x, am.y)), aL, aR);
-                            m = fmaf(fmaxf(aL, aR), e1, m);
+                    for (; sa != send; sa += 16u) {
+                        const float4 sgf = lds128(sa);
+                        const uint32_t sx = __float_as_uint(sgf.x), sz = __float_as_uint(sgf.z);
+                        const float xj = sgf.w + lane_f;
+                        const uint64_t xj2 = pack2(xj, xj);
+                        uint32_t ra = sx & 0x3ffffu;
+                        const uint32_t rend = ra + (sx >> 18) * (uint32_t)sizeof(Nh3Pair);
+                        float tpv = 0.0f;                            // -log2(e) * tau_j
+                        // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
+                        // whose own window test masks it off in this chunk
+#pragma unroll 1
+                        do {
+                            nh3_pair_term(tpv, ra, xj2);
+                            ra += (uint32_t)sizeof(Nh3Pair);
+                        } while (ra != rend);
+                        // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
+                        const float e1s = tpv * fmaf(tpv, fmaf(tpv, kC3, kC2), kC1);
+                        const float e1l = 1.0f - ex2_approx(tpv);
+                        const float e1 = tpv > kThr ? e1s : e1l;
+                        float aL, aR;
+                        const float4 am = lds128(__float_as_uint(sgf.y));          // {i_L, i_R, s_L, s_R}
+                        unpack2(fma2(pack2(am.z, am.w), xj2, pack2(am.x, am.y)), aL, aR);
+                        m = fmaf(fmaxf(aL, aR), e1, m);
+                        if ((int)sz < 0) {                           // last component of this chunk: residual
+                            if (WRITE_PRED) {
+                                const int j = (int)xj;
+                                if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = m;
+                            } else {
+                                // byte address of this lane's channel: the row base is 128-byte aligned
+                                const uint32_t off = (sz & 0x7fffffffu) | lane4;
+                                float d;
+                                if (staged) d = lds_f32(off);
+                                else d = __ldg(reinterpret_cast<const float *>(grow + off));
+                                const float r = d - m;
+                                acc = fmaf(r, r, acc);
+                            }
+                            m = 0.0f;
                         }
-                        if (WRITE_PRED) {
-                            const int j = ((sb + cc) << 5) + lane;
-                            if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = m;
-                        }
-                        const float r = d - m;
-                        acc = fmaf(r, r, acc);
                     }
                 }
                 if (have_data) {
@@ -541,7 +575,7 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     int max_lines = 1;
     for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
     a.npair = (max_lines >> 1) + 1;     // lines 0..NL (NL = the null line) in pairs of either parity
-    a.nkey = (max_lines + 3) & ~3;
+    a.nkey = a.n_chan > 1024 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
     auto kern = nf_nh3_kernel<MODEL, NC, WP, PT>;
     const size_t smem = nh3_smem_bytes<NC>(a);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;

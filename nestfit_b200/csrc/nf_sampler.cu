@@ -668,7 +668,7 @@ int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_
     NfLikeArgs a;
     std::memset(&a, 0, sizeof(a));
     const nf_pixels *px = s->px;
-    a.data = px->data; a.inv2s2 = px->inv2s2; a.params = params; a.pix_of_vec = pix; a.vecs_per_pix = 1;
+    a.data = px->data; a.inv2s2 = px->inv2s2; a.d2chunk = px->d2chunk; a.params = params; a.pix_of_vec = pix; a.vecs_per_pix = 1;
     a.B = B; a.B_dev = B_dev; a.pix_stride = (int64_t)px->n_spec * px->n_pad; a.lnL = lnl; a.pred = nullptr; a.param_f64 = 1;
     a.ncomp = s->ncomp; a.n_spec = px->n_spec; a.n_chan = px->n_chan; a.n_pad = px->n_pad;
     a.cold = (s->flags & NF_FLAG_COLD) != 0; a.lte = (s->flags & NF_FLAG_LTE) != 0;
