@@ -108,7 +108,7 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     px->n_pix = n_pix;
     px->n_spec = n_spec;
     px->n_chan = n_chan;
-    px->n_pad = ((n_chan + 31) / 32) * 32;
+    px->n_pad = ((n_chan + 63) / 64) * 64;      // the hyperfine kernel walks 64-channel chunks
     int rc = fill_meta(px, nu_min, nu_chan, trans_id, rest_freq);
     if (rc != NF_OK) { delete px; return rc; }
     cudaError_t e;

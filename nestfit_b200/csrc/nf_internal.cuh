@@ -46,7 +46,7 @@ struct nf_pixels {
     int device;
     int model;
     int64_t n_pix;
-    int n_spec, n_chan, n_pad;      // n_pad: channels per row in HBM (multiple of 32)
+    int n_spec, n_chan, n_pad;      // n_pad: channels per row in HBM (multiple of 64)
     float *data;                    // [n_pix][n_spec][n_pad]
     double *inv2s2;                 // [n_pix][n_spec]  1/(2 sigma^2)
     double *null_lnz;               // [n_pix]

@@ -1,7 +1,8 @@
 // Fused NH3 hyperfine synthesis + radiative transfer + chi-square kernel (sm_100a), v6.
 //
 // One warp scores one parameter vector against one pixel; lanes <-> channels in the
-// FP32 main loop (32-channel chunks).  Everything around the main loop is laid out so
+// FP32 main loop: 64-channel chunks, lane l owns channels 64 g + l and 64 g + l + 32, so that
+// every pair record fetched from shared memory serves four windowed Gaussians per lane.  Everything around the main loop is laid out so
 // that lanes are busy:
 //   S  set-up, batched over the warp's next few vectors: lanes <-> (vector, component,
 //      spectrum); partition function, main-line optical depth and the brightness
@@ -265,20 +266,26 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
     return v;
 }
 
-// Two windowed Gaussian terms (lines 2q+p and 2q+p+1) at channel coordinate xj (packed twice).
-__device__ __forceinline__ void nh3_pair_term(float &tp, uint32_t ra, uint64_t xj2)
+// Two hyperfine lines (2q+p and 2q+p+1) at the lane's two channels xa and xb = xa + 32 (each packed
+// twice): one record fetch, four windowed Gaussian terms.
+__device__ __forceinline__ void nh3_pair_term(float &tpa, float &tpb, uint32_t ra, uint64_t xa2, uint64_t xb2)
 {
     const float4 A = lds128(ra), B = lds128(ra + 16);
     const float2 H = lds64(ra + 32);
-    const uint64_t d2 = add2(xj2, pack2(A.x, A.y));                        // exact: multiples of 1/2
-    const uint64_t t2 = fma2(pack2(A.z, A.w), d2, pack2(B.x, B.y));
-    const uint64_t a2 = fma2(t2, d2, pack2(B.z, B.w));
-    float d0, d1, a0, a1;
-    unpack2(d2, d0, d1);
-    unpack2(a2, a0, a1);
-    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-    masked_sub(tp, e0, d0, H.x);
-    masked_sub(tp, e1, d1, H.y);
+    const uint64_t R2 = pack2(A.x, A.y), K2 = pack2(A.z, A.w), B2 = pack2(B.x, B.y), L2 = pack2(B.z, B.w);
+    const uint64_t da2 = add2(xa2, R2), db2 = add2(xb2, R2);              // exact: multiples of 1/2
+    const uint64_t ta2 = fma2(K2, da2, B2), tb2 = fma2(K2, db2, B2);
+    const uint64_t aa2 = fma2(ta2, da2, L2), ab2 = fma2(tb2, db2, L2);
+    float da0, da1, db0, db1, aa0, aa1, ab0, ab1;
+    unpack2(da2, da0, da1);
+    unpack2(db2, db0, db1);
+    unpack2(aa2, aa0, aa1);
+    unpack2(ab2, ab0, ab1);
+    const float ea0 = ex2_approx(aa0), ea1 = ex2_approx(aa1), eb0 = ex2_approx(ab0), eb1 = ex2_approx(ab1);
+    masked_sub(tpa, ea0, da0, H.x);
+    masked_sub(tpa, ea1, da1, H.y);
+    masked_sub(tpb, eb0, db0, H.x);
+    masked_sub(tpb, eb1, db1, H.y);
 }
 
 // ---- the fused kernel ---------------------------------------------------------
@@ -324,7 +331,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 
     const int n_spec = a.n_spec;
     const int ipv = NC * n_spec;
-    const int nchunks = (a.n_chan + 31) >> 5;
+    const int nchunks = (a.n_chan + 63) >> 6;        // 64-channel chunks (rows are padded to a multiple of 64)
     float lane_f;                 // kept in registers (volatile asm: never rematerialised inside the main loop)
     uint32_t lane4;
     asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(lane_f) : "r"(lane));
@@ -386,8 +393,8 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                         // chunk keys, ascending in the (frequency-sorted) line index.  An in-band line with an
                         // empty window keeps a nominal one-channel extent so that both keys stay sorted.
                         const int hi_n = max(hi, lo + 1);
-                        const int kE = below ? -1 : (inband ? (lo >> 5) : NH3_KEY_NEVER);
-                        const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 5) + 1 : NH3_KEY_NEVER);
+                        const int kE = below ? -1 : (inband ? (lo >> 6) : NH3_KEY_NEVER);
+                        const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 6) + 1 : NH3_KEY_NEVER);
                         float mR = 0.f, mk2 = 0.f, Bq = 0.f, Lq = -INFINITY, hh = -1.0f;
                         if (on) {
                             const int r2 = lo + hi - 1;                       // twice the window midpoint
@@ -438,7 +445,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                     // ---- T: work list of the super-block, lanes <-> chunks ----
                     int nseg;
                     {
-                        if (sb > 0) {   // later super-blocks (n_chan > 1024): recount from the stored keys
+                        if (sb > 0) {   // later super-blocks (n_chan > 2048): recount from the stored keys
                             for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
                             __syncwarp();
                             const int NL = sm.nlines, nitems = NC * NL;
@@ -486,63 +493,77 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                         nseg = __shfl_sync(NF_FULL, incl, 31);
                         int at = incl - n_mine;
                         const int g = sb + lane;
-                        const uint32_t xbits = __float_as_uint((float)(g << 5));
+                        const uint32_t xbits = __float_as_uint((float)(g << 6));
                         int left = n_mine;
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
                             if (ent[c] != 0u) {
                                 --left;
                                 sc.seg[at++] = make_uint4(ent[c], amp_addr + (uint32_t)(c * n_spec) * 16u,
-                                                          (srow + ((uint32_t)g << 7)) | (left == 0 ? 0x80000000u : 0u), xbits);
+                                                          (srow + ((uint32_t)g << 8)) | (left == 0 ? 0x80000000u : 0u), xbits);
                             }
                         }
                         // a chunk no line touches contributes its sum of d^2 (kept per pixel in HBM)
-                        if (have_data && n_mine == 0 && g < nchunks)
-                            acc += __ldg(a.d2chunk + (pix * n_spec + s) * (int64_t)(a.n_pad >> 5) + g);
+                        if (have_data && n_mine == 0 && g < nchunks) {
+                            const float2 q = __ldg(reinterpret_cast<const float2 *>(
+                                a.d2chunk + (pix * n_spec + s) * (int64_t)(a.n_pad >> 5)) + g);
+                            acc += q.x + q.y;
+                        }
                         __syncwarp();
                     }
                     // ---- M: main loop over the (chunk, component) records of this super-block ----
                     uint32_t sa = smem_u32(sc.seg);
                     const uint32_t send = sa + (uint32_t)nseg * 16u;
-                    float m = 0.0f;
+                    float ma = 0.0f, mb = 0.0f;
 #pragma unroll 1
                     for (; sa != send; sa += 16u) {
                         const float4 sgf = lds128(sa);
                         const uint32_t sx = __float_as_uint(sgf.x), sz = __float_as_uint(sgf.z);
-                        const float xj = sgf.w + lane_f;
-                        const uint64_t xj2 = pack2(xj, xj);
+                        const float xa = sgf.w + lane_f, xb = xa + 32.0f;
+                        const uint64_t xa2 = pack2(xa, xa), xb2 = pack2(xb, xb);
                         uint32_t ra = sx & 0x3ffffu;
                         const uint32_t rend = ra + (sx >> 18) * (uint32_t)sizeof(Nh3Pair);
-                        float tpv = 0.0f;                            // -log2(e) * tau_j
+                        float tpa = 0.0f, tpb = 0.0f;                // -log2(e) * tau at the lane's two channels
                         // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
                         // whose own window test masks it off in this chunk
 #pragma unroll 1
                         do {
-                            nh3_pair_term(tpv, ra, xj2);
+                            nh3_pair_term(tpa, tpb, ra, xa2, xb2);
                             ra += (uint32_t)sizeof(Nh3Pair);
                         } while (ra != rend);
                         // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
-                        const float e1s = tpv * fmaf(tpv, fmaf(tpv, kC3, kC2), kC1);
-                        const float e1l = 1.0f - ex2_approx(tpv);
-                        const float e1 = tpv > kThr ? e1s : e1l;
-                        float aL, aR;
+                        const uint64_t tp2 = pack2(tpa, tpb);
+                        float e1sa, e1sb;
+                        unpack2(mul2(tp2, fma2(tp2, fma2(tp2, pack2(kC3, kC3), pack2(kC2, kC2)), pack2(kC1, kC1))), e1sa, e1sb);
+                        const float e1la = 1.0f - ex2_approx(tpa), e1lb = 1.0f - ex2_approx(tpb);
+                        const float e1a = tpa > kThr ? e1sa : e1la, e1b = tpb > kThr ? e1sb : e1lb;
                         const float4 am = lds128(__float_as_uint(sgf.y));          // {i_L, i_R, s_L, s_R}
-                        unpack2(fma2(pack2(am.z, am.w), xj2, pack2(am.x, am.y)), aL, aR);
-                        m = fmaf(fmaxf(aL, aR), e1, m);
+                        float aLa, aRa, aLb, aRb;
+                        unpack2(fma2(pack2(am.z, am.w), xa2, pack2(am.x, am.y)), aLa, aRa);
+                        unpack2(fma2(pack2(am.z, am.w), xb2, pack2(am.x, am.y)), aLb, aRb);
+                        ma = fmaf(fmaxf(aLa, aRa), e1a, ma);
+                        mb = fmaf(fmaxf(aLb, aRb), e1b, mb);
                         if ((int)sz < 0) {                           // last component of this chunk: residual
                             if (WRITE_PRED) {
-                                const int j = (int)xj;
-                                if (j < a.n_chan) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = m;
+                                const int j = (int)xa;
+                                float *row = a.pred + (b * n_spec + s) * (int64_t)a.n_chan;
+                                if (j < a.n_chan) row[j] = ma;
+                                if (j + 32 < a.n_chan) row[j + 32] = mb;
                             } else {
-                                // byte address of this lane's channel: the row base is 128-byte aligned
+                                // byte address of this lane's first channel: the row base is 128-byte aligned
                                 const uint32_t off = (sz & 0x7fffffffu) | lane4;
-                                float d;
-                                if (staged) d = lds_f32(off);
-                                else d = __ldg(reinterpret_cast<const float *>(grow + off));
-                                const float r = d - m;
-                                acc = fmaf(r, r, acc);
+                                float da, db;
+                                if (staged) { da = lds_f32(off); db = lds_f32(off + 128u); }
+                                else {
+                                    da = __ldg(reinterpret_cast<const float *>(grow + off));
+                                    db = __ldg(reinterpret_cast<const float *>(grow + off + 128u));
+                                }
+                                const float ra_ = da - ma, rb_ = db - mb;
+                                acc = fmaf(ra_, ra_, acc);
+                                acc = fmaf(rb_, rb_, acc);
                             }
-                            m = 0.0f;
+                            ma = 0.0f;
+                            mb = 0.0f;
                         }
                     }
                 }
@@ -575,7 +596,7 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     int max_lines = 1;
     for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
     a.npair = (max_lines >> 1) + 1;     // lines 0..NL (NL = the null line) in pairs of either parity
-    a.nkey = a.n_chan > 1024 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
+    a.nkey = a.n_chan > 2048 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
     auto kern = nf_nh3_kernel<MODEL, NC, WP, PT>;
     const size_t smem = nh3_smem_bytes<NC>(a);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
