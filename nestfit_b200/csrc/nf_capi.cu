@@ -113,8 +113,7 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     if (rc != NF_OK) { delete px; return rc; }
     cudaError_t e;
     const size_t nrow = (size_t)n_pix * n_spec;
-    if ((e = nf_model_init_device_tables(device)) != cudaSuccess ||
-        (e = cudaMalloc(&px->data, nrow * px->n_pad * sizeof(float))) != cudaSuccess ||
+    if ((e = cudaMalloc(&px->data, nrow * px->n_pad * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&px->inv2s2, nrow * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&px->null_lnz, (size_t)n_pix * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&px->d2chunk, nrow * (px->n_pad / 32) * sizeof(float))) != cudaSuccess ||
@@ -190,10 +189,7 @@ int make_args(const nf_pixels *px, const void *params, int param_dtype, const in
     a->n_pad = px->n_pad;
     a->cold = (flags & NF_FLAG_COLD) != 0;
     a->lte = (flags & NF_FLAG_LTE) != 0;
-    for (int s = 0; s < px->n_spec; ++s) {
-        a->spec[s] = px->spec[s];
-        if (px->spec[s].para) a->need_para = 1; else a->need_ortho = 1;
-    }
+    for (int s = 0; s < px->n_spec; ++s) a->spec[s] = px->spec[s];
     return NF_OK;
 }
 

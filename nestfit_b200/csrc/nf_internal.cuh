@@ -20,7 +20,6 @@
 #define NF_WARPS_PER_CTA 8
 #define NF_THREADS (NF_WARPS_PER_CTA * 32)
 #define NF_TILE_VECS 64          // parameter vectors per CTA tile
-#define NF_MAX_LINES 32          // hyperfine lines per (component, spectrum) <= warp width
 #define NF_IEM_SIZE 1000         // 1/(e^x-1) table, nestfit/models/hyperfine.pyx:12
 
 // Per-spectrum constants prepared on the host in FP64.
@@ -37,7 +36,7 @@ struct NfSpecMeta {
     double tbg0, tbg1;  // 1/expm1(T0_j/Tcmb) ~= tbg0 + tbg1*j   ammonia.pyx:273-277
     float t0a, t0b;     // T0_j = t0a + t0b*j
     int line_off;       // first line in the global line tables
-    int nlines;         // hyperfine lines of this transition (<= NF_MAX_LINES)
+    int nlines;         // hyperfine lines of this transition
     int J;              // rotational level J (=K), 1..9
     int para;           // para (K % 3 != 0) or ortho
 };
@@ -86,7 +85,6 @@ struct NfLikeArgs {
     int param_f64;
     int ncomp, n_spec, n_chan, n_pad;
     int cold, lte;
-    int need_para, need_ortho;
     int tile_vecs;              // parameter vectors per CTA tile (0 -> NF_TILE_VECS)
     int npair;                  // hyperfine kernel: pair records per parity (set by the launcher)
     int nkey;                   // hyperfine kernel: line keys per component (set by the launcher)
@@ -96,9 +94,7 @@ struct NfLikeArgs {
 // launchers (nf_model.cu)
 cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st);          // nf_nh3.cu
 cudaError_t nf_launch_n2hp(const NfLikeArgs &a, cudaStream_t st);         // nf_nh3.cu (N2H+ front end)
-cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st);   // nf_model.cu (previous kernel, NF_NH3_LEGACY=1)
 cudaError_t nf_launch_gauss(const NfLikeArgs &a, cudaStream_t st);
-cudaError_t nf_model_init_device_tables(int device);
 cudaError_t nf_launch_null_lnz(const float *data, const double *inv2s2, double *out,
                                int64_t n_pix, int n_spec, int n_chan, int n_pad,
                                cudaStream_t st);

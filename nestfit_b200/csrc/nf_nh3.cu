@@ -618,12 +618,8 @@ static cudaError_t nh3_launch_nc(const NfLikeArgs &a, cudaStream_t st)
     return wp ? nh3_launch_one<MODEL, NC, true, float>(a, st) : nh3_launch_one<MODEL, NC, false, float>(a, st);
 }
 
-cudaError_t nf_launch_nh3_legacy(const NfLikeArgs &a, cudaStream_t st);
-
 cudaError_t nf_launch_nh3(const NfLikeArgs &a, cudaStream_t st)
 {
-    static const bool legacy = std::getenv("NF_NH3_LEGACY") != nullptr;
-    if (legacy) return nf_launch_nh3_legacy(a, st);
     cudaError_t e = nh3_init_device_tables();
     if (e) return e;
     switch (a.ncomp) {
