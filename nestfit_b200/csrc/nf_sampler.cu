@@ -348,9 +348,9 @@ __global__ void ns_propose_kernel(const NsDev D)
             D.chain_l[(int64_t)r * D.Kmax + k] = D.live_l[(int64_t)r * D.nlive_max + j];
             D.chain_moved[(int64_t)r * D.Kmax + k] = 0;
         }
+        ok = true;
         unit_ball(rng, d, y);
         const double sc = D.scale[r];
-        ok = true;
         for (int i = 0; i < d; ++i) {
             double v = 0.0;
             for (int j = 0; j <= i; ++j) v += B[d + i * d + j] * y[j];
@@ -452,17 +452,12 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     const double lnshell = log(-expm1(-1.0 / (double)nl));
     const int64_t c0 = (int64_t)D.cand_off[w];  // candidate slots of this run in this iteration
     int mode = D.mode[r];
-    // random-walk cohorts of all runs start on the same lock-steps (multiples of `walks`), so that
-    // the serial insertion work at a cohort's end falls on one lock-step in `walks` for every run
-    if (mode == 2 && (D.lock + 1) % D.walks == 0) {
-        mode = 1;
-        if (lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
-    }
     if (mode != 1) {
         int n_ok = 0, n_acc = 0;
         for (int k = 0; k < K && !S.done; ++k) {
             const double *cu = D.cand_u + (c0 + k) * d;
-            if (cu[0] == cu[0]) { ++nev; ++n_ok; }
+            if (!(cu[0] == cu[0])) continue;      // no valid draw inside the unit cube: not a candidate
+            ++nev; ++n_ok;
             if (try_insert(D, r, nl, lane, lnshell, cu, D.cand_th + (c0 + k) * d, D.cand_l[c0 + k], S, LL)) ++n_acc;
         }
         // windowed acceptance rate; fall back to the random walk when rejection sampling stalls
@@ -471,11 +466,17 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
             if (!(D.flags & 2) && mode == 0 && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
                 mode = 2;                      // hand over to the random walk at the next aligned lock-step
                 if (lane == 0) D.mode[r] = 2;
-                if ((D.lock + 1) % D.walks == 0 && lane == 0) { D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3; }
             }
             ea = 0; ep = 0;
         }
         if (lane == 0) { D.eff_acc[r] = ea; D.eff_prop[r] = ep; }
+        // Random-walk cohorts of all runs start on the same lock-steps (multiples of `walks`), so that
+        // the serial insertion work at a cohort's end falls on one lock-step in `walks` for every run.
+        // This step's candidates were rejection-sampling proposals and have been consumed as such;
+        // the next lock-step opens the first cohort (coh_step = 0 makes the proposal kernel start chains).
+        if (mode == 2 && (D.lock + 1) % D.walks == 0 && lane == 0) {
+            D.mode[r] = 1; D.coh_step[r] = 0; D.scale[r] = 0.3;
+        }
     } else {
         int step = D.coh_step[r];
         double lstar;
@@ -808,6 +809,13 @@ int nf_ns_run(nf_sampler *s)
                                               s->krun, s->cand_off, K, s->Kmax, (int64_t)s->cfg.target_batch);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = (int)e;
+    }
+    if (rc == NF_OK && getenv("NF_NS_DEBUG")) {
+        std::vector<double> ll((size_t)R * NL);
+        cudaMemcpy(ll.data(), s->live_l, ll.size() * 8, cudaMemcpyDeviceToHost);
+        double mn = 1e300, mx = -1e300; size_t nz = 0, nn = 0;
+        for (double v : ll) { if (v != v) { ++nn; continue; } mn = v < mn ? v : mn; mx = v > mx ? v : mx; if (v == 0.0) ++nz; }
+        fprintf(stderr, "[ns] initial live lnL: min %.6g max %.6g zeros %zu nans %zu of %zu\n", mn, mx, nz, nn, ll.size());
     }
     int n_act = rc == NF_OK ? s->n_act_host[0] : 0;
     int lock = 0;

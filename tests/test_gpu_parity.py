@@ -133,7 +133,7 @@ def _random_problem(nb, rng, ncomp, n_pix, n_chan, dv):
 
 
 @pytest.mark.parametrize("ncomp,n_chan,dv", [(1, 1000, 0.07), (2, 379, 0.158), (3, 1000, 0.07), (4, 1024, 0.05),
-                                             (3, 33, 1.0)])
+                                             (3, 33, 1.0), (2, 100, 0.5), (2, 65, 0.9), (3, 4500, 0.02)])
 def test_nh3_random_batch_vs_oracle(nb, ncomp, n_chan, dv):
     """Ragged, unsorted pixel assignment; tiles straddling pixels; odd channel counts."""
     rng = np.random.default_rng(100 + ncomp + n_chan)

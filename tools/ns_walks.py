@@ -14,7 +14,8 @@ stack = make_synth_stack((2, 2), ut, ncomp_map=np.full((2, 2), nc), n_chan=1000,
 lon, lat = (a.ravel() for a in np.indices((2, 2)))
 data, noise, valid = stack.block_arrays(lon, lat)
 blk = nb.PixelBlock("ammonia", [c.xarr for c in stack.cubes], data, noise, trans_ids=[1, 2])
-for pix in (0, 1):
+pixels = [int(v) for v in sys.argv[4].split(',')] if len(sys.argv) > 4 else [0, 1]
+for pix in pixels:
     for w in walks_list:
         ns = NestedSamplingBatch(blk, ut, nc, pix_ids=np.full(R, pix), nlive=300, tol=1.0, n_prop=32, seed=5, walks=w)
         t0 = time.perf_counter(); r = ns.run(); dt = time.perf_counter() - t0
