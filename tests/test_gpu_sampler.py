@@ -169,3 +169,25 @@ def test_run_multinest_dropin_contract(nb):
     k, nn, maxL = 6.0, 760.0, group.attrs['max_loglike']
     assert group.attrs['BIC'] == pytest.approx(np.log(nn) * k - 2 * maxL)
     assert group.attrs['AICc'] == pytest.approx(2 * k - 2 * maxL + (2 * k**2 + 2 * k) / (nn - k - 1))
+
+
+def test_consecutive_samplers_and_max_loglike_sanity(nb):
+    """Several samplers in one process, many copies of one pixel (so each run gets the large
+    per-step proposal counts of a wave's tail from the start): every run must terminate, and
+    no run may report a likelihood above what the truth itself reaches plus the parameter
+    count (a run whose random-walk chains were started from stale memory reported lnL = 0
+    and never finished)."""
+    from nestfit_b200.sampler import NestedSamplingBatch
+    blk, ut, truth = nh3_problem(nb, 2, n_pix=2, noise=0.15)
+    lnl_truth = blk.loglike(np.repeat(truth[None], 2, axis=0), 2, pix_of_vec=np.array([0, 1], dtype=np.int32))
+    for rep in range(3):
+        pix = np.full(24, rep % 2, dtype=np.int32)
+        ns = NestedSamplingBatch(blk, ut, 2, pix_ids=pix, nlive=150, tol=1.0, n_prop=32, seed=40 + rep, max_iter=40000)
+        res = ns.run()
+        assert not res["truncated"].any()
+        assert np.isfinite(res["lnZ"]).all()
+        assert np.all(res["max_loglike"] < lnl_truth[rep % 2] + 12 + 20)
+        assert np.all(res["max_loglike"] > lnl_truth[rep % 2] - 60)
+        # best-fit vectors are finite physical parameters
+        assert np.isfinite(res["bestfit"]).all()
+        ns.close()
