@@ -281,6 +281,7 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(times[0]), float(times[1])
 
+    gauss_result = run_gauss(nb, lib, _lib, dev, rank, dist) if not args.no_gauss else None
     cube_result = None
     if args.cube_size > 0:
         del d_params, d_lnl, flush
@@ -364,11 +365,59 @@ def run_ours(args):
             "max_abs_dlnL_vs_gpu": float(err.max()),
             "parity_ok": bool((err <= 1e-3 + 2e-6 * np.abs(lnl_cpu)).all()),
         }
+    if gauss_result is not None:
+        line["gauss_loglike"] = gauss_result
     if cube is not None:
         line["cube_fit"] = cube
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_gauss(nb, lib, _lib, dev, rank, dist):
+    """Secondary metric (BASELINE configs[4]): Gaussian model, 8 components over 4096 channels, 2^18 vectors per
+    GPU against 256 pixels (replicated data, disjoint vector slices); device-resident evals/s, max over ranks."""
+    import torch
+    from oracle import oracle as orc        # axis helper + work accounting only
+    from nestfit_b200.parallel import max_over_ranks
+    B, n_chan, ncomp, n_pix = 1 << 18, 4096, 8, 256
+    rng = np.random.default_rng(5 + rank)
+    v = (np.arange(n_chan) - 2047.5) * 0.05
+    x = np.sort(orc.NU[0] * (1 - v / orc.CKMS))
+    P = np.concatenate([np.sort(rng.uniform(-90, 90, (B, ncomp)), axis=1), rng.uniform(0.2, 3, (B, ncomp)),
+                        rng.uniform(0.1, 5, (B, ncomp))], axis=1).astype(np.float32)
+    scratch = nb.PixelBlock("gaussian", [x], np.zeros((1, 1, n_chan), np.float32), 0.1, rest_freq=orc.NU[0], device=dev)
+    clean = scratch.predict(P[:n_pix], ncomp)
+    scratch.close()
+    data = clean + np.random.default_rng(6).normal(0, 0.1, clean.shape).astype(np.float32)
+    blk = nb.PixelBlock("gaussian", [x], data, 0.1, rest_freq=orc.NU[0], device=dev)
+    d_p = torch.from_numpy(P).to(f"cuda:{dev}")
+    d_l = torch.empty(B, dtype=torch.float64, device=f"cuda:{dev}")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        _lib.check(lib.nf_gauss_loglike(blk.handle, d_p.data_ptr(), _lib.NF_F32, None, B // n_pix, B, ncomp,
+                                        d_l.data_ptr(), st), "nf_gauss_loglike")
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_it = 10
+    e0.record()
+    for _ in range(n_it):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1) / n_it, dist, device=f"cuda:{dev}")
+    blk.close()
+    if rank != 0:
+        return None
+    world = 1 if dist is None else dist.get_world_size()
+    cnt = orc.gauss_batch(x, orc.NU[0], P[:2048].astype(np.float64), ncomp, count=True)["counters"] / 2048.0
+    return {"metric": "Gaussian loglike evals/s (8-comp, 4096 ch)", "value": world * B / (ms * 1e-3), "unit": "evals/s",
+            "ms_per_launch": ms, "vectors_per_gpu": B, "windowed_gaussians_per_eval": float(cnt[0]), "scaling": "weak"}
 
 
 def run_cube_fit(nb, args, rank, world, dev, dist):
@@ -528,6 +577,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-model metric")
     ap.add_argument("--cube-size", type=int, default=64,
                     help="side of the per-GPU synthetic cube of the secondary cube-fit metric (0 = skip)")
     args = ap.parse_args()
