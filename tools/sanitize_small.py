@@ -25,4 +25,24 @@ x = np.sort(orc.NU[0] * (1 - v / orc.CKMS))
 Pg = np.concatenate([rng.uniform(-30, 30, (40, 5)), rng.uniform(0.3, 3, (40, 5)), rng.uniform(0.1, 4, (40, 5))], axis=1)
 gb = nb.PixelBlock("gaussian", [x], rng.normal(0, 0.1, (2, 1, 300)).astype(np.float32), 0.1, rest_freq=orc.NU[0])
 assert np.isfinite(gb.loglike(Pg, 5, vecs_per_pix=20)).all() and np.isfinite(gb.predict(Pg, 5)).all()
+# wide band (more than one 2048-channel super-block), odd channel count, (3,3) ortho transition
+xw = [orc.bench_axis(1, 2300, 0.03), orc.bench_axis(3, 2300, 0.03)]
+Pw = ut.transform_batch(rng.uniform(size=(40, 12)), 2)
+Pw[~np.isfinite(Pw).all(axis=1)] = Pw[0]
+Pw[:, 10:] = 0.5
+bw = nb.PixelBlock("ammonia", xw, rng.normal(0, 0.1, (2, 2, 2300)).astype(np.float32), 0.1, trans_ids=[1, 3])
+assert np.isfinite(bw.loglike(Pw, 2, vecs_per_pix=20)).all() and np.isfinite(bw.predict(Pw[:3], 2)).all()
+bw.close()
+# N2H+ (45-line (3-2) transition), ragged pixel map, sampler with the tail scheduling (few runs, large K)
+xn = [np.sort(orc.N2HP_NU[t - 1] * (1 - (np.arange(333) - 166.0) * 0.1 / orc.CKMS)) for t in (1, 3)]
+Pn = np.concatenate([np.sort(rng.uniform(-6, 6, (50, 3)), axis=1), rng.uniform(3, 20, (50, 3)), rng.uniform(-1.5, 1.2, (50, 3)),
+                     rng.uniform(0.08, 1.5, (50, 3))], axis=1)
+bn = nb.PixelBlock("diazenylium", xn, rng.normal(0, 0.1, (3, 2, 333)).astype(np.float32), 0.1, trans_ids=[1, 3])
+assert np.isfinite(bn.loglike(Pn, 3, pix_of_vec=rng.integers(0, 3, 50).astype(np.int32))).all()
+assert np.isfinite(bn.predict(Pn[:4], 3)).all()
+bn.close()
+blk = nb.PixelBlock("ammonia", xs, rng.normal(0, 0.1, (2, 2, 200)).astype(np.float32), 0.1, trans_ids=[1, 2])
+ns = NestedSamplingBatch(blk, ut, 2, pix_ids=np.array([0, 1, 1]), nlive=40, tol=1.0, n_prop=8, seed=2, max_iter=400,
+                         method='rwalk', walks=6)
+r = ns.run(); assert np.isfinite(r['lnZ']).all(); ns.close(); blk.close()
 print("sanitize run ok")
