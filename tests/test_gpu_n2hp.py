@@ -94,3 +94,38 @@ def test_diazenylium_runner_contract(nb, n2hp_golden):
     s = dz.DiazenyliumSpectrum(x, np.zeros(800), 0.1, trans_id=1)
     dz.nnhp_predict(s, g["params1_2"][0])
     assert_spectra(s.get_spec(), g["pred1_2"][0])
+
+
+def test_n2hp_cube_fit_through_cubefitter(nb, tmp_path):
+    """The N2H+ model through the whole drop-in path: CubeFitter -> batched sampler (n_model = 4) ->
+    store, with the reference's escalation rule (main.py:450-469)."""
+    from nestfit_b200.models import diazenylium as dz
+    from nestfit_b200.main import DataCube, CubeStack
+    from nestfit_b200.store import HdfStore
+    rng = np.random.default_rng(9)
+    n_chan = 300
+    x = np.sort(orc.N2HP_NU[0] * (1 - (np.arange(n_chan) - 0.5 * (n_chan - 1)) * 0.12 / orc.CKMS))
+    size = 200
+    u = np.linspace(0, 1, size)
+    flat = np.ones(size) / size
+    ut = nb.PriorTransformer(np.array([
+        nb.OrderedPrior(nb.Distribution(8 * u - 4, flat), 0), nb.Prior(nb.Distribution(17 * u + 3, flat), 1),
+        nb.Prior(nb.Distribution(2.5 * u - 1.5, flat), 2), nb.Prior(nb.Distribution(1.0 * u + 0.1, flat), 3)],
+        dtype=object))
+    truth = np.array([0.7, 8.0, 0.3, 0.35])
+    clean = orc.n2hp_batch([x], [1], truth[None], 1, want_pred=True)["pred"][0, 0]
+    data = np.zeros((2, 2, n_chan))
+    data[0] = clean + rng.normal(0, 0.1, (2, n_chan))        # signal in the first row, noise in the second
+    data[1] = rng.normal(0, 0.1, (2, n_chan))
+    stack = CubeStack([DataCube.from_arrays(data, x, 0.1, trans_id=1)])
+    fitter = nb.CubeFitter(stack, ut, dz.DiazenyliumRunner, ncomp_max=2, mn_kwargs={'nlive': 100}, lnZ_thresh=11, seed=3)
+    res = fitter.fit_cube(str(tmp_path / 'n2hp'), nproc=1)[0]
+    nbest = res['nbest'].reshape(2, 2)
+    assert np.all(nbest[0] == 1) and np.all(nbest[1] == 0)
+    store = HdfStore(str(tmp_path / 'n2hp'))
+    assert store.hdf.attrs['model_name'] == 'diazenylium' and store.hdf.attrs['n_params'] == 4
+    run = store.hdf['/pix/0/1/1']
+    assert run.attrs['n_params'] == 4 and run['marginals'].shape == (15, 4)
+    bf = run['bestfit_params'][...]
+    assert abs(bf[0] - 0.7) < 0.1 and abs(bf[3] - 0.35) < 0.1
+    store.close()
