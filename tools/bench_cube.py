@@ -11,6 +11,7 @@ ap.add_argument('--size', type=int, default=64)
 ap.add_argument('--ncomp-max', type=int, default=3)
 ap.add_argument('--nprop', type=int, default=32)
 ap.add_argument('--chan', type=int, default=1000)
+ap.add_argument('--noise-grad', action='store_true', help='spatially varying noise 0.05..0.3 K (configs[3])')
 ap.add_argument('--streams', type=int, default=1)
 ap.add_argument('--pps', type=int, default=1024)
 args = ap.parse_args()
@@ -19,7 +20,10 @@ n = args.size
 lon, lat = np.indices((n, n))
 ncomp_map = ((lon // max(1, n // 4)) + (lat // max(1, n // 4))) % 4        # spatial blocks of 0..3 components
 t0 = time.perf_counter()
-stack = make_synth_stack((n, n), ut, ncomp_map=ncomp_map, n_chan=args.chan, dv=0.07, noise=0.1, seed=1)
+noise = 0.1
+if args.noise_grad:      # smooth gradient across the map (NoiseMap semantics, main.py:39-65)
+    noise = 0.05 + 0.25 * (lon + lat) / (2.0 * (n - 1))
+stack = make_synth_stack((n, n), ut, ncomp_map=ncomp_map, n_chan=args.chan, dv=0.07, noise=noise, seed=1)
 t_build = time.perf_counter() - t0
 fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=args.ncomp_max, lnZ_thresh=11,
                        mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=args.nprop,
