@@ -116,13 +116,15 @@ struct Philox {
         const uint64_t v = ((a << 32) | b) >> 11;
         return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
     }
+    // two standard normals (Box-Muller in FP32: proposal directions do not need more)
     __device__ void normal2(double &z0, double &z1)
     {
-        const double u1 = uniform(), u2 = uniform();
-        const double r = sqrt(-2.0 * log(u1));
-        double s, c2;
-        sincospi(2.0 * u2, &s, &c2);
-        z0 = r * c2; z1 = r * s;
+        const float u1 = ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * __logf(u1));
+        float s, c2;
+        sincospif(2.0f * u2, &s, &c2);
+        z0 = (double)(r * c2); z1 = (double)(r * s);
     }
 };
 
@@ -299,7 +301,7 @@ __device__ void unit_ball(Philox &rng, int d, double *y)
         y[j] = z0; n2 += z0 * z0;
         if (j + 1 < d) { y[j + 1] = z1; n2 += z1 * z1; }
     }
-    const double rad = pow(rng.uniform(), 1.0 / (double)d) / sqrt(n2);
+    const double rad = (double)exp2f(__log2f((float)rng.uniform()) / (float)d) / sqrt(n2);
     for (int j = 0; j < d; ++j) y[j] *= rad;
 }
 
@@ -371,6 +373,8 @@ __global__ void ns_propose_kernel(const NsDev D)
 // Running state of one run held in registers by every lane of its warp.
 struct RunState {
     double lnZ, H, lmax;
+    double mn;          // current worst live log-likelihood and its slot (recomputed after every insertion)
+    int im;
     int it, nd;
     bool done;
 };
@@ -398,9 +402,8 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
                            const double *ct, double lc, RunState &S, double *LL)
 {
     const int d = D.d;
-    double mn;
-    int im;
-    warp_argmin(LL, nl, lane, mn, im);
+    const double mn = S.mn;
+    const int im = S.im;
     if (!(lc > mn)) return false;          // rejected (also NaN)
     const double lnw = -(double)S.it / (double)nl + lnshell;
     const double lw = mn + lnw;
@@ -425,6 +428,7 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
     for (int j = lane; j < d; j += 32) { lu[j] = cu[j]; lt[j] = ct[j]; }
     if (lane == 0) { LL[im] = lc; D.live_l[(int64_t)r * D.nlive_max + im] = lc; }
     __syncwarp();
+    warp_argmin(LL, nl, lane, S.mn, S.im);
     ++S.it;
     S.lmax = fmax(S.lmax, lc);
     // MultiNest `tol`: largest possible remaining contribution L_max X_i
@@ -446,6 +450,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     for (int p = lane; p < nl; p += 32) LL[p] = D.live_l[(int64_t)r * D.nlive_max + p];
     __syncwarp();
     RunState S;
+    warp_argmin(LL, nl, lane, S.mn, S.im);
     S.lnZ = D.lnZ[r]; S.H = D.H[r]; S.lmax = D.lmax[r]; S.it = D.it[r]; S.nd = D.n_dead[r]; S.done = false;
     int64_t nev = D.n_eval[r];
     // ln(1 - exp(-1/nlive)): ln of the prior-mass shell X_{i-1} - X_i relative to X_{i-1}
@@ -481,8 +486,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
         int step = D.coh_step[r];
         double lstar;
         if (step == 0) {                        // a new cohort: threshold = current worst live point
-            int im;
-            warp_argmin(LL, nl, lane, lstar, im);
+            lstar = S.mn;
             if (lane == 0) { D.lstar[r] = lstar; D.coh_acc[r] = 0; }
         } else {
             lstar = D.lstar[r];
