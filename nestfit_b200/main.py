@@ -208,11 +208,15 @@ class CubeFitter:
 
     def __init__(self, stack, utrans, runner_cls, runner_kwargs=None, lnZ_thresh=11, ncomp_max=2, mn_kwargs=None,
                  nlive_snr_fact=5, n_prop=32, max_pixels_per_wave=16384, seed=1234, store_posteriors=True,
-                 n_streams=1, pixels_per_stream=1024):
+                 n_streams=1, pixels_per_stream=1024, retry_margin=10.0, retry_chi2_sigma=6.0):
         """Same arguments as the reference (main.py:388-421) plus the batching knobs
         `n_prop` (proposals per pixel per lock-step iteration), `max_pixels_per_wave`
         (pixels in flight per device wave), `n_streams` (host threads / CUDA streams that
-        escalate sub-blocks of `pixels_per_stream` pixels concurrently) and `seed`."""
+        escalate sub-blocks of `pixels_per_stream` pixels concurrently), `seed`, and `retry_margin`: an
+        N-component run whose maximum likelihood falls more than this below the (N-1)-component run's
+        has lost the dominant mode and is repeated once with twice the live points (None: never), as is a
+        run (N >= 2) that fails the evidence threshold while its best chi-square is more than
+        `retry_chi2_sigma` sigma above the channel count."""
         self.stack = stack
         self.utrans = utrans
         self.runner_cls = runner_cls
@@ -227,6 +231,8 @@ class CubeFitter:
         self.max_pixels_per_wave = max_pixels_per_wave
         self.n_streams = n_streams
         self.pixels_per_stream = pixels_per_stream
+        self.retry_margin = retry_margin
+        self.retry_chi2_sigma = retry_chi2_sigma
         self.seed = seed
         self.store_posteriors = store_posteriors
         self.stats = {}
@@ -272,6 +278,7 @@ class CubeFitter:
             nbest = np.zeros(vidx.size, dtype=np.int32)
             out['lnZ'][w0 + vidx, 0] = null
             evals = []
+            n_retried, n_rescued = [0], [0]
             lock = threading.Lock()
 
             def fit_sub(active, tag):
@@ -282,6 +289,8 @@ class CubeFitter:
                     if verbose:
                         print(f'-- wave {w0}.{tag}: N = {ncomp}: {active.size} pixels')
                     kw = {k: v for k, v in self.runner_kwargs.items() if k in ('cold', 'lte')}
+                    if self.mn_kwargs.get('walks'):
+                        kw['walks'] = int(self.mn_kwargs['walks'])       # random-walk steps per new point
                     ns = NestedSamplingBatch(blk, self.utrans, ncomp, pix_ids=active, nlive=nlive[active],
                                              tol=self.mn_kwargs['tol'], efr=self.mn_kwargs['efr'], n_prop=self.n_prop,
                                              seed=self.seed + 7919 * ncomp + w0 + 104729 * tag,
@@ -290,6 +299,37 @@ class CubeFitter:
                     evals.append(int(res['n_evals'].sum()))
                     assert np.isfinite(res['lnZ']).all()           # main.py:463
                     gi = w0 + vidx[active]
+                    # Lost-mode guard (a few per cent of 3-component runs at nlive ~ 300 end in a secondary
+                    # mode).  Two symptoms: (i) an N-component model can always reproduce the (N-1)-component
+                    # fit, so a best likelihood clearly *below* the previous wave's is a lost mode; (ii) the
+                    # run does not pass the evidence threshold although its best fit is far from the noise
+                    # (chi-square many sigma above the channel count, the noise being known).  Such runs are
+                    # repeated once with twice the live points and a new seed; the repeat replaces the run
+                    # when its evidence is higher.
+                    owner = [(ns, r) for r in range(active.size)]
+                    ns_retry = None
+                    if ncomp >= 2 and self.retry_margin is not None:
+                        suspect = res['max_loglike'] < out['max_loglike'][gi, ncomp - 1] - self.retry_margin
+                        if self.retry_chi2_sigma is not None:
+                            chi2_max = n_chan_tot + self.retry_chi2_sigma * np.sqrt(2.0 * n_chan_tot)
+                            suspect |= ((-2.0 * res['max_loglike'] > chi2_max) &
+                                        (res['lnZ'] - old_lnZ[active] < self.lnZ_thresh))
+                        lost = np.flatnonzero(suspect)
+                        if lost.size:
+                            ns_retry = NestedSamplingBatch(blk, self.utrans, ncomp, pix_ids=active[lost],
+                                                           nlive=2 * nlive[active[lost]], tol=self.mn_kwargs['tol'],
+                                                           efr=self.mn_kwargs['efr'], n_prop=self.n_prop,
+                                                           seed=self.seed + 7919 * ncomp + w0 + 104729 * tag + 15485863,
+                                                           max_iter=self.mn_kwargs.get('maxiter', 1_000_000), **kw)
+                            res2 = ns_retry.run()
+                            evals.append(int(res2['n_evals'].sum()))
+                            better = np.flatnonzero(res2['lnZ'] > res['lnZ'][lost])
+                            for key in ('lnZ', 'lnZ_err', 'max_loglike', 'n_samples'):
+                                res[key][lost[better]] = res2[key][better]
+                            for j in better:
+                                owner[lost[j]] = (ns_retry, int(j))
+                            n_retried[0] += int(lost.size)
+                            n_rescued[0] += int(better.size)
                     out['lnZ'][gi, ncomp] = res['lnZ']
                     out['lnZ_err'][gi, ncomp] = res['lnZ_err']
                     out['max_loglike'][gi, ncomp] = res['max_loglike']
@@ -299,7 +339,7 @@ class CubeFitter:
                             for r, a in enumerate(active):
                                 g = group_root.require_group(f'/pix/{lon[vidx[a]]}/{lat[vidx[a]]}')
                                 sub = g.create_group(f'{ncomp}')
-                                attrs, dsets = ns.products(r, null[a], n_chan_tot)
+                                attrs, dsets = owner[r][0].products(owner[r][1], null[a], n_chan_tot)
                                 for k, v in attrs.items():
                                     sub.attrs[k] = v
                                 for k, v in dsets.items():
@@ -307,6 +347,8 @@ class CubeFitter:
                                         continue
                                     sub.create_dataset(k, data=v)
                     ns.close()
+                    if ns_retry is not None:
+                        ns_retry.close()
                     improved = res['lnZ'] - old_lnZ[active] >= self.lnZ_thresh     # main.py:464-469
                     old_lnZ[active[improved]] = res['lnZ'][improved]
                     nbest[active[improved]] = ncomp
@@ -343,6 +385,8 @@ class CubeFitter:
                 if errors:
                     raise errors[0]
             n_evals += sum(evals)
+            out['n_retried'] = out.get('n_retried', 0) + n_retried[0]
+            out['n_rescued'] = out.get('n_rescued', 0) + n_rescued[0]
             out['nbest'][w0 + vidx] = nbest
             if group_root is not None:
                 for a in range(vidx.size):
