@@ -115,9 +115,21 @@ class CpuArm:
         self.pool.join()
 
 
+CKMS = 299792.458
+NU_NH3 = (23.6944955e9, 23.722633335e9)      # (1,1), (2,2) rest frequencies [Hz], ammonia.pyx:69-70
+
+# Algorithmic work per evaluation of this exact (seeded) workload, counted once with the reference's FP64
+# window rule by tools/count_work.py (the C oracle, test infrastructure) on the 8192-vector sample
+# `default_rng(7).choice(B_TOTAL, 8192)`; tests/test_gpu_bench_work.py re-counts and pins these numbers.
+WORK_N_GAUSS = 8891.77197265625      # windowed Gaussian exponentials per eval (n_g)
+WORK_N_RT = 2447.415283203125        # radiative-transfer exponentials per eval (n_rt)
+WORK_GAUSS_MODEL = 2577.03125            # windowed Gaussians per eval of the 8 x 4096 Gaussian-model workload
+
+
 def axes():
-    from oracle import oracle as orc   # axis helper only (numpy arithmetic)
-    return [orc.bench_axis(1, N_CHAN, DV), orc.bench_axis(2, N_CHAN, DV)]
+    """Config-2 axes: v_j = (j - (N-1)/2) dv, x = sort(nu0 (1 - v/c))  (SURVEY.md 8d)."""
+    v = (np.arange(N_CHAN) - 0.5 * (N_CHAN - 1)) * DV
+    return [np.sort(nu0 * (1.0 - v / CKMS)) for nu0 in NU_NH3]
 
 
 # --------------------------------------------------------------------------
@@ -297,11 +309,8 @@ def run_ours(args):
     e2e_value = evals * n_e2e / e2e_s
 
     # ---- roofline of the dominant (only) kernel --------------------------------
-    from oracle import oracle as orc        # work accounting by the reference's window rule, FP64, on the host
     ns = 8192
-    pick = np.random.default_rng(7).choice(B_TOTAL, size=ns, replace=False)
-    cnt = orc.nh3_batch(xs, [1, 2], P32[pick].astype(np.float64), NCOMP, count=True)["counters"] / float(ns)
-    n_g, n_rt = float(cnt[0]), float(cnt[1])
+    n_g, n_rt = WORK_N_GAUSS, WORK_N_RT
     sfu_per_eval = n_g + n_rt + N_SETUP_SFU
     flop_per_eval = 5 * n_g + 8 * n_rt + 3 * 2 * N_CHAN + 30 * NCOMP * (18 + 21)
     mufu = _lib.C.c_double()
@@ -325,7 +334,8 @@ def run_ours(args):
         "frac": ach / peak, "traffic": traffic,
         "peak_source": "measured live by nf_measure_peaks (MUFU.EX2 / FFMA register loops, this box)",
         "work_per_eval": {"n_gauss": n_g, "n_rt": n_rt, "n_setup": N_SETUP_SFU, "sfu_ops": sfu_per_eval,
-                          "fp32_flop": flop_per_eval, "counted_on": f"{ns}-vector host sample (oracle, FP64 window rule)"},
+                          "fp32_flop": flop_per_eval, "counted_on": f"{ns}-vector host sample of this seeded workload (tools/count_work.py: reference window "
+                                        "rule in FP64; pinned by tests/test_gpu_bench_work.py)"},
         "fp32": {"achieved_gflops": ach_fp32, "peak_gflops": ffma.value, "frac": ach_fp32 / ffma.value},
         "hbm": {"algorithmic_bytes_per_launch": B_TOTAL * (4 * 6 * NCOMP + 8) + N_PIX * 2 * 1024 * 4,
                 "note": "80 B per eval + 8 KB per pixel staged once per CTA tile; not the bound"},
@@ -378,19 +388,18 @@ def run_gauss(nb, lib, _lib, dev, rank, dist):
     """Secondary metric (BASELINE configs[4]): Gaussian model, 8 components over 4096 channels, 2^18 vectors per
     GPU against 256 pixels (replicated data, disjoint vector slices); device-resident evals/s, max over ranks."""
     import torch
-    from oracle import oracle as orc        # axis helper + work accounting only
     from nestfit_b200.parallel import max_over_ranks
     B, n_chan, ncomp, n_pix = 1 << 18, 4096, 8, 256
     rng = np.random.default_rng(5 + rank)
     v = (np.arange(n_chan) - 2047.5) * 0.05
-    x = np.sort(orc.NU[0] * (1 - v / orc.CKMS))
+    x = np.sort(NU_NH3[0] * (1 - v / CKMS))
     P = np.concatenate([np.sort(rng.uniform(-90, 90, (B, ncomp)), axis=1), rng.uniform(0.2, 3, (B, ncomp)),
                         rng.uniform(0.1, 5, (B, ncomp))], axis=1).astype(np.float32)
-    scratch = nb.PixelBlock("gaussian", [x], np.zeros((1, 1, n_chan), np.float32), 0.1, rest_freq=orc.NU[0], device=dev)
+    scratch = nb.PixelBlock("gaussian", [x], np.zeros((1, 1, n_chan), np.float32), 0.1, rest_freq=NU_NH3[0], device=dev)
     clean = scratch.predict(P[:n_pix], ncomp)
     scratch.close()
     data = clean + np.random.default_rng(6).normal(0, 0.1, clean.shape).astype(np.float32)
-    blk = nb.PixelBlock("gaussian", [x], data, 0.1, rest_freq=orc.NU[0], device=dev)
+    blk = nb.PixelBlock("gaussian", [x], data, 0.1, rest_freq=NU_NH3[0], device=dev)
     d_p = torch.from_numpy(P).to(f"cuda:{dev}")
     d_l = torch.empty(B, dtype=torch.float64, device=f"cuda:{dev}")
     st = torch.cuda.current_stream().cuda_stream
@@ -415,9 +424,8 @@ def run_gauss(nb, lib, _lib, dev, rank, dist):
     if rank != 0:
         return None
     world = 1 if dist is None else dist.get_world_size()
-    cnt = orc.gauss_batch(x, orc.NU[0], P[:2048].astype(np.float64), ncomp, count=True)["counters"] / 2048.0
     return {"metric": "Gaussian loglike evals/s (8-comp, 4096 ch)", "value": world * B / (ms * 1e-3), "unit": "evals/s",
-            "ms_per_launch": ms, "vectors_per_gpu": B, "windowed_gaussians_per_eval": float(cnt[0]), "scaling": "weak"}
+            "ms_per_launch": ms, "vectors_per_gpu": B, "windowed_gaussians_per_eval": WORK_GAUSS_MODEL, "scaling": "weak"}
 
 
 def run_cube_fit(nb, args, rank, world, dev, dist):
