@@ -272,6 +272,13 @@ class PriorTransformer:
                    "nf_prior_transform_host")
         return u
 
+    def __getstate__(self):
+        """Device handles are per process: a pickled copy (one worker per GPU, main.py:515-523)
+        rebuilds its own plan on first use."""
+        state = self.__dict__.copy()
+        state['_handles'] = {}
+        return state
+
     def __del__(self):
         try:
             lib = _lib.load()

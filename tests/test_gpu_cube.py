@@ -51,3 +51,36 @@ def test_fit_cube_small(nb, tmp_path):
     v = run['bestfit_params'][:2]
     assert abs(v[0] + 1.5) < 0.2 and abs(v[1] - 1.5) < 0.2
     store.close()
+
+
+def test_fit_cube_two_gpus(nb, tmp_path):
+    """fit_cube(nproc=2): one spawned process per GPU, contiguous pixel blocks, one chunk file each,
+    linked into the table (main.py:476-526, 313-322).  Skipped on single-GPU boxes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from nestfit_b200.synth import make_synth_stack
+    from nestfit_b200.store import HdfStore
+    from nestfit_b200.models import ammonia
+    ut = nb.get_irdc_priors()
+    ncomp_map = np.zeros((4, 4), dtype=int)
+    ncomp_map[2:] = 1
+    stack = make_synth_stack((4, 4), ut, ncomp_map=ncomp_map, n_chan=400, dv=0.158, noise=0.1, seed=4)
+    blk = nb.PixelBlock("ammonia", [c.xarr for c in stack.cubes], np.zeros((1, 2, 400), np.float32), 1.0,
+                        trans_ids=[1, 2])
+    t1 = np.array([[0.3, 14.0, 6.0, 14.6, 0.45, 0.0]])
+    clean = blk.predict(t1, 1)[0]
+    rng = np.random.default_rng(8)
+    for c in (0, 1):
+        stack.cubes[c].data[2:] = clean[c] + rng.normal(0, 0.1, (2, 4, 400))
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 100}, seed=6)
+    fitter.fit_cube(str(tmp_path / 'cube2'), nproc=2)
+    store = HdfStore(str(tmp_path / 'cube2'))
+    assert store.nchunks == 2 and all(p.exists() for p in store.chunk_paths)
+    groups = list(store.iter_pix_groups())
+    assert len(groups) == 16
+    nbest = np.full((4, 4), -9)
+    for g in groups:
+        nbest[g.attrs['i_lon'], g.attrs['i_lat']] = g.attrs['nbest']
+    assert np.all(nbest[:2] == 0) and np.all(nbest[2:] == 1)
+    store.close()

@@ -124,3 +124,23 @@ def test_two_rank_gloo_partition_and_gather(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "GLOO_OK 2" in res.stdout
+
+
+def test_cubefitter_pickles_for_spawned_workers(nb):
+    """fit_cube(nproc > 1) hands the fitter to one spawned process per GPU (main.py:515-523): the
+    fitter, its priors and the store must pickle (device handles are rebuilt per process)."""
+    import pickle
+    from nestfit_b200.synth import velocity_axis_hz
+    from nestfit_b200.main import DataCube, CubeStack
+    from nestfit_b200.models import ammonia
+    ut = nb.get_irdc_priors()
+    ut._handles = {0: object()}          # stands in for a live device handle
+    x = [velocity_axis_hz(1, 100, 0.3), velocity_axis_hz(2, 100, 0.3)]
+    stack = CubeStack([DataCube.from_arrays(np.zeros((2, 2, 100)), x[t], 0.1, trans_id=t + 1) for t in range(2)])
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=2)
+    try:
+        clone = pickle.loads(pickle.dumps(fitter))
+    finally:
+        ut._handles = {}
+    assert clone.utrans._handles == {} and clone.utrans.n_param == 6 and clone.ncomp_max == 2
+    assert clone.stack.cubes[1].trans_id == 2
