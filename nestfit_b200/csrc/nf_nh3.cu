@@ -1,20 +1,25 @@
-// Fused NH3 hyperfine synthesis + radiative transfer + chi-square kernel (sm_100a), v6.
+// Fused hyperfine synthesis + radiative transfer + chi-square kernel (sm_100a) for the NH3
+// (J,K) inversion lines and N2H+ J = 1-0, 2-1, 3-2.
 //
-// One warp scores one parameter vector against one pixel; lanes <-> channels in the
-// FP32 main loop: 64-channel chunks, lane l owns channels 64 g + l and 64 g + l + 32, so that
-// every pair record fetched from shared memory serves four windowed Gaussians per lane.  Everything around the main loop is laid out so
-// that lanes are busy:
+// One warp scores one parameter vector against one pixel.  In the FP32 main loop lanes <->
+// channels on 64-channel chunks: lane l owns channels 64 g + l and 64 g + l + 32, so every pair
+// record fetched from shared memory serves four windowed Gaussians per lane.  Everything around
+// the main loop is laid out so that lanes are busy:
 //   S  set-up, batched over the warp's next few vectors: lanes <-> (vector, component,
 //      spectrum); partition function, main-line optical depth and the brightness
-//      amplitude in FP64                                   (ammonia.pyx:289-361)
+//      amplitude in FP64                                   (ammonia.pyx:289-361,
+//                                                           diazenylium.pyx:140-154)
 //   L  per (vector, spectrum): lanes <-> (component, hyperfine line), flattened; window
 //      [lo, hi) with the reference's floor rule in FP64    (hyperfine.pyx:68-96)
-//   T  per-chunk dispatch table: lanes <-> chunks; the lines touching a chunk are a
-//      contiguous run of the frequency-sorted records (counting + warp scan)
-//   M  main loop: two lines per trip in packed FP32x2 (FADD2/FFMA2), MUFU.EX2, one
-//      compare per line (windows are stored symmetric about their own midpoint), then
-//      the radiative transfer and the residual per chunk   (hyperfine.pyx:98-113,
-//      core.pyx:522-530)
+//   T  work list of a super-block: lanes <-> chunks; the lines touching a chunk are a
+//      contiguous run of the frequency-sorted records (counting + warp scan); the non-empty
+//      (chunk, component) runs are compacted into a flat list
+//   M  main loop over that list: two lines x two channels per trip in packed FP32x2
+//      (FADD2/FFMA2), MUFU.EX2, one compare per term (windows are stored symmetric about
+//      their own midpoint), then the radiative transfer and, on the last component of a
+//      chunk, the residual                                 (hyperfine.pyx:98-113,
+//                                                           core.pyx:522-530)
+//   Chunks no line touches are never visited: their sum of d^2 comes from a per-pixel table.
 //
 // Arithmetic identities used (all exact up to FP32 rounding):
 //   tau_j = sum_i tau_main w_i exp(-k_i (j - c_i)^2) is accumulated as
@@ -22,6 +27,7 @@
 //   with log2(log2(e) tau_main w_i) folded into L_i, so exp(-tau_j) = 2^tp_j.
 //   FastExp semantics (nestfit/core/fastexp.c:234-283): exp(-x) of the float-rounded
 //   argument -> MUFU.EX2; Taylor-3 branch below 2^-5 kept for 1 - exp(-tau).
+//   A negative main-line optical depth (outside every prior) gives NaN, not the reference's sign.
 
 #include <cmath>
 #include <cstdio>
