@@ -272,6 +272,22 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
     return v;
 }
 
+// Two hyperfine lines at one channel x (packed twice): the run touches only one half of the chunk.
+__device__ __forceinline__ void nh3_pair_term1(float &tp, uint32_t ra, uint64_t x2)
+{
+    const float4 A = lds128(ra), B = lds128(ra + 16);
+    const float2 H = lds64(ra + 32);
+    const uint64_t d2 = add2(x2, pack2(A.x, A.y));                         // exact: multiples of 1/2
+    const uint64_t t2 = fma2(pack2(A.z, A.w), d2, pack2(B.x, B.y));
+    const uint64_t a2 = fma2(t2, d2, pack2(B.z, B.w));
+    float d0, d1, a0, a1;
+    unpack2(d2, d0, d1);
+    unpack2(a2, a0, a1);
+    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+    masked_sub(tp, e0, d0, H.x);
+    masked_sub(tp, e1, d1, H.y);
+}
+
 // Two hyperfine lines (2q+p and 2q+p+1) at the lane's two channels xa and xb = xa + 32 (each packed
 // twice): one record fetch, four windowed Gaussian terms.
 __device__ __forceinline__ void nh3_pair_term(float &tpa, float &tpb, uint32_t ra, uint64_t xa2, uint64_t xb2)
@@ -416,8 +432,13 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                         }
                         if (act) {
                             if (nkey) keys[c * nkey + i] = make_short2((short)kE, (short)kF);
-                            atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u);          // table counts of super-block 0
-                            atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x10000u);
+                            // counts of super-block 0, four 8-bit fields per (component, chunk): lines starting
+                            // here, lines ended before here, lines starting here in the chunk's first half,
+                            // lines whose last channel lies in the second half of the chunk before this one
+                            const uint32_t tA = (inband && (lo & 63) < 32) ? 0x10000u : 0u;
+                            const uint32_t tB = (inband && ((hi_n - 1) & 63) >= 32) ? 0x1000000u : 0u;
+                            atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u + tA);
+                            atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x100u + tB);
                             // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
                             // of the other parity that starts one line earlier
                             float *pb = pairf + c * (2 * npair * 12);
@@ -464,17 +485,21 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                                     if (NC > 3) c += t >= 3 * NL;
                                     const int i = t - c * NL;
                                     const short2 ky = keys[c * nkey + i];
-                                    atomicAdd(&cw[c * 36 + min(max((int)ky.x - sb, 0), 32)], 1u);
-                                    atomicAdd(&cw[c * 36 + min(max((int)ky.y - sb, 0), 32)], 0x10000u);
+                                    // (half-chunk flags are not kept with the keys: both halves count as touched)
+                                    atomicAdd(&cw[c * 36 + min(max((int)ky.x - sb, 0), 32)], 0x10001u);
+                                    atomicAdd(&cw[c * 36 + min(max((int)ky.y - sb, 0), 32)], 0x1000100u);
                                 }
                             }
                             __syncwarp();
                         }
-                        uint32_t v[NC];
+                        uint32_t v[NC], vraw[NC], vnext[NC];
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) v[c] = cw[c * 36 + lane];
+                        for (int c = 0; c < NC; ++c) {
+                            v[c] = vraw[c] = cw[c * 36 + lane];
+                            vnext[c] = cw[c * 36 + lane + 1];
+                        }
                         __syncwarp();
-                        uint32_t ent[NC];
+                        uint32_t ent[NC], half[NC];
                         int n_mine = 0;
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
@@ -484,11 +509,17 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                                 if (lane >= o) v[c] += u;
                             }
                             // the lines touching chunk g are the run [#ended(g), #started(g)) of the sorted records
-                            const int end = (int)(v[c] & 0xffffu), first = (int)(v[c] >> 16);
+                            const int end = (int)(v[c] & 0xffu), first = (int)((v[c] >> 8) & 0xffu);
                             const int cnt = end - first;
                             const uint32_t addr = pair_addr + (uint32_t)(((c * 2 + (first & 1)) * npair + (first >> 1)) * (int)sizeof(Nh3Pair));
                             ent[c] = cnt > 0 ? (addr | ((uint32_t)((cnt + 1) >> 1) << 18)) : 0u;
                             n_mine += cnt > 0;
+                            // which 32-channel halves of the chunk the run touches: a line that started in an earlier
+                            // chunk covers the first half, one that goes on into a later chunk the second half
+                            const int start_here = (int)(vraw[c] & 0xffu), end_next = first + (int)((vnext[c] >> 8) & 0xffu);
+                            const bool hitA = (end - start_here - first) > 0 || ((vraw[c] >> 16) & 0xffu) != 0u;
+                            const bool hitB = (end - end_next) > 0 || (vnext[c] >> 24) != 0u;
+                            half[c] = (hitA && !hitB) ? 0x20000000u : ((hitB && !hitA) ? 0x40000000u : 0u);
                         }
                         int incl = n_mine;
 #pragma unroll
@@ -506,7 +537,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                             if (ent[c] != 0u) {
                                 --left;
                                 sc.seg[at++] = make_uint4(ent[c], amp_addr + (uint32_t)(c * n_spec) * 16u,
-                                                          (srow + ((uint32_t)g << 8)) | (left == 0 ? 0x80000000u : 0u), xbits);
+                                                          (srow + ((uint32_t)g << 8)) | half[c] | (left == 0 ? 0x80000000u : 0u), xbits);
                             }
                         }
                         // a chunk no line touches contributes its sum of d^2 (kept per pixel in HBM)
@@ -529,21 +560,37 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                         const uint64_t xa2 = pack2(xa, xa), xb2 = pack2(xb, xb);
                         uint32_t ra = sx & 0x3ffffu;
                         const uint32_t rend = ra + (sx >> 18) * (uint32_t)sizeof(Nh3Pair);
+                        const float4 am = lds128(__float_as_uint(sgf.y));          // {i_L, i_R, s_L, s_R}
                         float tpa = 0.0f, tpb = 0.0f;                // -log2(e) * tau at the lane's two channels
-                        // two lines per trip (packed FP32x2); a trailing odd slot holds the next line,
-                        // whose own window test masks it off in this chunk
+                        if ((sz & 0x60000000u) == 0u) {
+                            // the run touches both 32-channel halves: two lines x two channels per trip (packed
+                            // FP32x2; a trailing odd slot holds the next line, whose own window test masks it off)
 #pragma unroll 1
-                        do {
-                            nh3_pair_term(tpa, tpb, ra, xa2, xb2);
-                            ra += (uint32_t)sizeof(Nh3Pair);
-                        } while (ra != rend);
-                        // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270)
+                            do {
+                                nh3_pair_term(tpa, tpb, ra, xa2, xb2);
+                                ra += (uint32_t)sizeof(Nh3Pair);
+                            } while (ra != rend);
+                        } else if (sz & 0x40000000u) {
+                            // the run touches the second half only: two lines x one channel per trip
+#pragma unroll 1
+                            do {
+                                nh3_pair_term1(tpb, ra, xb2);
+                                ra += (uint32_t)sizeof(Nh3Pair);
+                            } while (ra != rend);
+                        } else {
+#pragma unroll 1
+                            do {
+                                nh3_pair_term1(tpa, ra, xa2);
+                                ra += (uint32_t)sizeof(Nh3Pair);
+                            } while (ra != rend);
+                        }
+                        // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270); a half the run does
+                        // not touch has tp = 0 and contributes exactly 0
                         const uint64_t tp2 = pack2(tpa, tpb);
                         float e1sa, e1sb;
                         unpack2(mul2(tp2, fma2(tp2, fma2(tp2, pack2(kC3, kC3), pack2(kC2, kC2)), pack2(kC1, kC1))), e1sa, e1sb);
                         const float e1la = 1.0f - ex2_approx(tpa), e1lb = 1.0f - ex2_approx(tpb);
                         const float e1a = tpa > kThr ? e1sa : e1la, e1b = tpb > kThr ? e1sb : e1lb;
-                        const float4 am = lds128(__float_as_uint(sgf.y));          // {i_L, i_R, s_L, s_R}
                         float aLa, aRa, aLb, aRb;
                         unpack2(fma2(pack2(am.z, am.w), xa2, pack2(am.x, am.y)), aLa, aRa);
                         unpack2(fma2(pack2(am.z, am.w), xb2, pack2(am.x, am.y)), aLb, aRb);
@@ -557,7 +604,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
                                 if (j + 32 < a.n_chan) row[j + 32] = mb;
                             } else {
                                 // byte address of this lane's first channel: the row base is 128-byte aligned
-                                const uint32_t off = (sz & 0x7fffffffu) | lane4;
+                                const uint32_t off = (sz & 0x3ffffu) | lane4;
                                 float da, db;
                                 if (staged) { da = lds_f32(off); db = lds_f32(off + 128u); }
                                 else {
