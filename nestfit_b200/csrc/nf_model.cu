@@ -3,7 +3,8 @@
 //
 // One warp scores one parameter vector against one pixel:
 //   lanes <-> components during the FP64 set-up (window with the reference's floor rule),
-//   lanes <-> channels (32-channel chunks) during the FP32 main loop.
+//   lanes <-> channels during the FP32 main loop: 64-channel chunks, lane l owns channels 64 g + l
+//   and 64 g + l + 32 (packed FP32x2 across the two channels).
 // A CTA (8 warps) works on a tile of consecutive vectors; the pixel of the tile's first vector
 // is staged once in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).  Components
 // are unordered and have unequal widths, so the components touching a chunk are found by ballot;
@@ -85,7 +86,7 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
 
     const int ncomp = a.ncomp;
     const int ndim = 3 * ncomp;
-    const int nchunks = (a.n_chan + 31) >> 5;
+    const int nchunks = (a.n_chan + 63) >> 6;        // 64-channel chunks (rows are padded to a multiple of 64)
     const NfSpecMeta &sm = a.spec[0];
     const double nu_min = sm.nu_min, inv_chan = sm.inv_chan, f0 = sm.nu0;
     const float lane_f = (float)lane;
@@ -144,7 +145,7 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
             // chunks [sb, sb+32) touched by this lane's component, and by any component
             uint32_t cm = 0u;
             {
-                int c_lo = (lo >> 5) - sb, c_hi = ((hi - 1) >> 5) - sb;
+                int c_lo = (lo >> 6) - sb, c_hi = ((hi - 1) >> 6) - sb;
                 if (on && c_hi >= 0 && c_lo < 32) {
                     c_lo = max(c_lo, 0);
                     c_hi = min(c_hi, 31);
@@ -154,32 +155,50 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
             uint32_t un = __reduce_or_sync(NF_FULL, cm);
             if (have_data) {          // a chunk no component touches contributes its sum of d^2
                 const int g = sb + lane;
-                if (g < nchunks && !((un >> lane) & 1u)) acc += __ldg(a.d2chunk + pix * (int64_t)(a.n_pad >> 5) + g);
+                if (g < nchunks && !((un >> lane) & 1u)) {
+                    const float2 q = __ldg(reinterpret_cast<const float2 *>(a.d2chunk + pix * (int64_t)(a.n_pad >> 5)) + g);
+                    acc += q.x + q.y;
+                }
             }
             while (un) {
                 const int cc = __ffs(un) - 1;
                 un &= un - 1;
                 uint32_t lm = __ballot_sync(NF_FULL, (cm >> cc) & 1u);
-                const int j0 = (sb + cc) << 5;
-                const float xj = (float)j0 + lane_f;
-                float m = 0.0f;
+                const int j0 = (sb + cc) << 6;
+                const float xa = (float)j0 + lane_f;
+                const uint64_t x2 = pack2(xa, xa + 32.0f);
+                float ma = 0.0f, mb = 0.0f;
                 while (lm) {          // components are unordered: walk the set bits
                     const int i = __ffs(lm) - 1;
                     lm &= lm - 1;
                     const uint32_t ra = rec_addr + (uint32_t)i * (uint32_t)sizeof(GaussRec);
                     const float4 A = gauss_lds128(ra);
                     const float h = gauss_lds_f32(ra + 16);
-                    const float d = xj + A.x;                   // exact: multiples of 1/2
-                    const float t = fmaf(A.y, d, A.z);
-                    const float e = ex2_approx(t * d);          // 2^(-k2 (d^2 - 2 phi' d)); 2^(-k2 phi'^2) is in A.w
-                    if (fabsf(d) <= h) m = fmaf(A.w, e, m);
+                    const uint64_t d2 = add2(x2, pack2(A.x, A.x));             // exact: multiples of 1/2
+                    const uint64_t t2 = fma2(pack2(A.y, A.y), d2, pack2(A.z, A.z));
+                    float da, db, ea, eb;
+                    unpack2(d2, da, db);
+                    unpack2(mul2(t2, d2), ea, eb);      // -k2 (d^2 - 2 phi' d) log2(e); 2^(-k2 phi'^2) is in A.w
+                    ea = ex2_approx(ea);
+                    eb = ex2_approx(eb);
+                    if (fabsf(da) <= h) ma = fmaf(A.w, ea, ma);
+                    if (fabsf(db) <= h) mb = fmaf(A.w, eb, mb);
                 }
                 if (WRITE_PRED) {
-                    if (j0 + lane < a.n_chan) prow[j0 + lane] = m;
+                    if (j0 + lane < a.n_chan) prow[j0 + lane] = ma;
+                    if (j0 + lane + 32 < a.n_chan) prow[j0 + lane + 32] = mb;
                 } else {
-                    const float d = staged ? gauss_lds_f32(srow + (uint32_t)j0 * 4u) : __ldg(grow + j0);
-                    const float r = d - m;
-                    acc = fmaf(r, r, acc);
+                    float da, db;
+                    if (staged) {
+                        da = gauss_lds_f32(srow + (uint32_t)j0 * 4u);
+                        db = gauss_lds_f32(srow + (uint32_t)j0 * 4u + 128u);
+                    } else {
+                        da = __ldg(grow + j0);
+                        db = __ldg(grow + j0 + 32);
+                    }
+                    const float ra_ = da - ma, rb_ = db - mb;
+                    acc = fmaf(ra_, ra_, acc);
+                    acc = fmaf(rb_, rb_, acc);
                 }
             }
         }
