@@ -208,15 +208,16 @@ class CubeFitter:
 
     def __init__(self, stack, utrans, runner_cls, runner_kwargs=None, lnZ_thresh=11, ncomp_max=2, mn_kwargs=None,
                  nlive_snr_fact=5, n_prop=32, max_pixels_per_wave=16384, seed=1234, store_posteriors=True,
-                 n_streams=1, pixels_per_stream=1024, retry_margin=10.0, retry_chi2_sigma=6.0):
+                 n_streams=1, pixels_per_stream=1024, retry_margin=None, retry_chi2_sigma=6.0):
         """Same arguments as the reference (main.py:388-421) plus the batching knobs
         `n_prop` (proposals per pixel per lock-step iteration), `max_pixels_per_wave`
         (pixels in flight per device wave), `n_streams` (host threads / CUDA streams that
-        escalate sub-blocks of `pixels_per_stream` pixels concurrently), `seed`, and `retry_margin`: an
-        N-component run whose maximum likelihood falls more than this below the (N-1)-component run's
-        has lost the dominant mode and is repeated once with twice the live points (None: never), as is a
-        run (N >= 2) that fails the evidence threshold while its best chi-square is more than
-        `retry_chi2_sigma` sigma above the channel count."""
+        escalate sub-blocks of `pixels_per_stream` pixels concurrently), `seed`, and the optional lost-mode
+        guard `retry_margin` (default None = off, one run per (pixel, ncomp) like the reference; e.g. 10):
+        an N-component run whose maximum likelihood falls more than this below the (N-1)-component run's
+        has lost the dominant mode and is repeated once with twice the live points, as is a run (N >= 2)
+        that fails the evidence threshold while its best chi-square is more than `retry_chi2_sigma` sigma
+        above the channel count.  The repeats are a small extra wave per ncomp (~1-2 s of latency each)."""
         self.stack = stack
         self.utrans = utrans
         self.runner_cls = runner_cls

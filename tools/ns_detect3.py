@@ -15,7 +15,7 @@ stack = make_synth_stack((n, n), ut, ncomp_map=np.full((n, n), 3), n_chan=1000, 
 idx, T = stack.truths[3]
 fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=3, lnZ_thresh=11,
                        mn_kwargs={'nlive': nlive0, 'tol': 1.0, 'efr': 0.3, 'walks': walks}, nlive_snr_fact=snr_fact, n_prop=32,
-                       retry_margin=(10.0 if len(sys.argv) <= 5 else None))
+                       retry_margin=(10.0 if len(sys.argv) > 5 else None))
 blocks = nb.get_block_indices((n, n), 1)
 res = fitter.fit_block(blocks[0], device=0)
 lon, lat = blocks[0]
