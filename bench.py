@@ -456,10 +456,51 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
     if rank != 0:
         return None
     agree = float((nbest.reshape(shape) == ncomp_map).mean())
-    return {"metric": "cube pixels/s fit (ncomp 1-3 evidence model selection)", "value": shape[0] * shape[1] / secs,
-            "unit": "pixels/s", "seconds": secs, "cube": [shape[0], shape[1], 2, N_CHAN], "scaling": "weak",
-            "nlive": "100 + 5*SNR", "tol": 1.0, "likelihood_evals_per_pixel_max_rank": evals / (n * n),
-            "nbest_matches_truth": agree}
+    out = {"metric": "cube pixels/s fit (ncomp 1-3 evidence model selection)", "value": shape[0] * shape[1] / secs,
+           "unit": "pixels/s", "seconds": secs, "cube": [shape[0], shape[1], 2, N_CHAN], "scaling": "weak",
+           "nlive": "100 + 5*SNR", "tol": 1.0, "likelihood_evals_per_pixel_max_rank": evals / (n * n),
+           "nbest_matches_truth": agree}
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cube_cpu_baseline(stack, ut, shape, nbest.reshape(shape))
+    return out
+
+
+def _cube_cpu_worker(ix):
+    from oracle import ns_port
+    xs, packed, data, noise = _W["cube"]
+    t0 = time.perf_counter()
+    r = ns_port.fit_pixel(xs, [1, 2], data[ix], noise[ix], packed, ncomp_max=3, lnZ_thresh=11, nlive=100,
+                          nlive_snr_fact=5, tol=1.0, efr=0.3, n_prop=32, seed=1000 + ix)
+    return r["nbest"], r["n_evals"], time.perf_counter() - t0
+
+
+def cube_cpu_baseline(stack, ut, shape, nbest_gpu):
+    """CPU baseline of the cube-fit metric: the same batched nested-sampling scheme and ncomp
+    escalation as a numpy port (oracle/ns_port.py) scored with the C oracle likelihood, one pixel per host core
+    (MultiNest, the reference's sampler, is an external Fortran library that is not available)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_tot = shape[0] * shape[1]
+    # one pixel per core, spread over the cube so that every true ncomp (0..3, in blocks) is represented
+    flat = (np.arange(cores) * (n_tot / cores) + 0.37 * n_tot / cores).astype(int) % n_tot
+    lon, lat = np.unravel_index(flat, shape)
+    data, noise, _ = stack.block_arrays(lon, lat)
+    _W["cube"] = ([np.asarray(c.xarr, dtype=np.float64) for c in stack.cubes], ut.pack(),
+                  np.asarray(data, dtype=np.float64), np.asarray(noise, dtype=np.float64))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cube_cpu_worker, range(cores), chunksize=1)
+    wall = time.perf_counter() - t0
+    nb_cpu = np.array([r[0] for r in res])
+    # throughput of a cube of many such pixels with every core kept busy (the wall time of this small sample is
+    # set by its slowest pixel and would understate the CPU)
+    busy = float(np.sum([r[2] for r in res]))
+    return {"value": len(res) * cores / busy, "unit": "pixels/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} pixels spread over the cube, one per core (numpy port of the sampler + C oracle "
+                      "likelihood, same nlive/tol/efr/escalation)",
+            "wall_seconds": wall, "likelihood_evals_per_pixel": float(np.mean([r[1] for r in res])),
+            "cpu_seconds_per_pixel": float(np.mean([r[2] for r in res])),
+            "nbest_agrees_with_gpu": float((nb_cpu == nbest_gpu[lon, lat]).mean())}
 
 
 def _with_device(nb, dev):

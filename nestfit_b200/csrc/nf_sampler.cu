@@ -151,7 +151,7 @@ __global__ void ns_init_live_kernel(double *live_u, double *live_th, int64_t n_r
 
 __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32_t *n_dead, int32_t *it,
                                      int32_t *done, int64_t *n_eval, int32_t *act, const int32_t *nlive,
-                                     const double *live_l, int64_t n_run, int nlive_max, int32_t *mode,
+                                     double *live_l, int64_t n_run, int nlive_max, int32_t *mode,
                                      int32_t *coh_step, int32_t *coh_acc, int32_t *eff_acc, int32_t *eff_prop,
                                      double *scale, int start_mode)
 {
@@ -162,7 +162,9 @@ __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32
     act[r] = (int32_t)r;
     double m = -INFINITY;
     for (int p = 0; p < nlive[r]; ++p) {
-        const double l = live_l[r * nlive_max + p];
+        double l = live_l[r * nlive_max + p];
+        // a draw the priors map to NaN scores NaN: treat it as MultiNest's logZero (it dies first, weight 0)
+        if (!(l == l)) { l = -INFINITY; live_l[r * nlive_max + p] = l; }
         if (l > m) m = l;
     }
     lmax[r] = m;

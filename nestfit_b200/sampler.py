@@ -115,6 +115,9 @@ class NestedSamplingBatch:
         lnw = np.empty(n)
         _lib.check(_lib.load().nf_ns_posterior(self.handle, run, n, _lib.ptr(th), _lib.ptr(lnl), _lib.ptr(lnw)),
                    "nf_ns_posterior")
+        keep = lnl > -np.inf          # logZero points (NaN prior draws among the first live set) carry no weight
+        if not keep.all():
+            th, lnl, lnw = th[keep], lnl[keep], lnw[keep]
         w = np.exp(lnl + lnw - res["lnZ"][run])
         return np.concatenate([th.astype(np.float64), lnl[:, None], w[:, None]], axis=1)
 

@@ -1,0 +1,189 @@
+"""
+TEST INFRASTRUCTURE -- not part of the product path.
+
+CPU restatement (numpy) of the batched nested-sampling scheme of
+nestfit_b200/csrc/nf_sampler.cu for ONE run, scored with the C oracle likelihood
+(oracle/nf_oracle.c).  It stands where the reference has MultiNest
+(nestfit/core/core.pyx:727-823 -> MultiNest `run`, cmultinest.pxd:5-33), which is an
+external Fortran library absent from /root/reference: "parity unpinned" -- there is no
+golden ln Z to compare with, so this port serves two purposes only:
+  * an independent implementation the CUDA sampler's ln Z is compared with
+    statistically (tests/test_gpu_sampler.py), and
+  * the CPU baseline of the cube-fit metric ("the same batched-NS
+    algorithm run on CPU with the oracle likelihood"), timed by bench.py.
+Only tests/ and bench.py's cpu_baseline leg may import this module.
+
+Scheme (same as the CUDA driver): live set of `nlive` unit-cube points; per step K
+candidates drawn uniformly from the bounding ellipsoid of the live set (enlarged to the
+larger of 1.2 x the bounding volume and X_i / efr; the unit cube while that volume is
+>= 1/2) are consumed in order against the current worst live point; once the windowed
+acceptance falls below 1 / (1.2 walks) the run switches to cohorts of K constrained
+random walks of `walks` steps in the ellipsoid's metric (step size adapted towards an
+acceptance of 1/2).  Dead points carry prior mass X_{i-1} - X_i, X_i = exp(-i / nlive);
+termination ln(Z + L_max X_i) - ln Z < tol; the live points are added with X_i / nlive.
+"""
+import math
+
+import numpy as np
+
+
+def _logaddexp(a, b):
+    if a == -np.inf:
+        return b
+    if b == -np.inf:
+        return a
+    m = max(a, b)
+    return m + math.log1p(math.exp(-abs(a - b)))
+
+
+def _unit_ball(rng, n, d):
+    z = rng.standard_normal((n, d))
+    r = rng.uniform(size=n) ** (1.0 / d) / np.sqrt((z * z).sum(axis=1))
+    return z * r[:, None]
+
+
+def _bound(U, it, nlive, efr):
+    """mean, scaled lower Cholesky factor, use_cube flag of the live set's bounding ellipsoid."""
+    d = U.shape[1]
+    mean = U.mean(axis=0)
+    cov = np.cov(U, rowvar=False).reshape(d, d) + 1e-12 * np.eye(d)
+    try:
+        L = np.linalg.cholesky(cov)
+    except np.linalg.LinAlgError:
+        return mean, np.eye(d), True
+    y = np.linalg.solve(L, (U - mean).T)
+    f = float((y * y).sum(axis=0).max())
+    lndet = float(np.log(np.diag(L)).sum())
+    lnVd = 0.5 * d * math.log(math.pi) - math.lgamma(0.5 * d + 1.0)
+    lnV_bound = lnVd + 0.5 * d * math.log(f) + lndet + math.log(1.2) if f > 0 else -np.inf
+    lnV = max(lnV_bound, -it / nlive - math.log(efr))
+    scale = math.exp((lnV - lnVd - lndet) / d)
+    use_cube = lnV > math.log(0.5) or not (f > 0) or not math.isfinite(scale)
+    return mean, scale * L, use_cube
+
+
+def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None, seed=0, max_iter=1_000_000,
+                    rwalk=False):
+    """score(U[B, ndim]) -> lnL[B] (prior transform inside; NaN = not acceptable).
+    `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk').
+    Returns dict(lnZ, lnZ_err, max_loglike, n_iter, n_evals, n_samples)."""
+    rng = np.random.default_rng(seed)
+    d, K = ndim, n_prop
+    walks = walks or 20 + d
+    U = rng.uniform(size=(nlive, d))
+    LL = np.asarray(score(U), dtype=np.float64).copy()
+    LL[~(LL == LL)] = -np.inf
+    st = dict(lnZ=-np.inf, H=0.0, lmax=float(LL.max()), it=0, nd=0, done=False)
+    n_evals = nlive
+    lnshell = math.log(-math.expm1(-1.0 / nlive))
+
+    def try_insert(u, lc):
+        im = int(np.argmin(LL))
+        mn = float(LL[im])
+        if not lc > mn:
+            return False
+        lnw = -st['it'] / nlive + lnshell
+        lw = mn + lnw
+        new = _logaddexp(st['lnZ'], lw)
+        if new > -np.inf:
+            t1 = math.exp(lw - new) * mn
+            t2 = math.exp(st['lnZ'] - new) * (st['H'] + st['lnZ']) if st['lnZ'] > -np.inf else 0.0
+            st['H'] = t1 + t2 - new
+        st['lnZ'] = new
+        st['nd'] += 1
+        U[im] = u
+        LL[im] = lc
+        st['it'] += 1
+        st['lmax'] = max(st['lmax'], lc)
+        if _logaddexp(st['lnZ'], st['lmax'] - st['it'] / nlive) - st['lnZ'] < tol or st['it'] >= max_iter:
+            st['done'] = True
+        return True
+
+    mode, ea, ep, sc = (1 if rwalk else 0), 0, 0, 0.3
+    while not st['done']:
+        mean, B, use_cube = _bound(U, st['it'], nlive, efr)
+        if mode == 0:
+            if use_cube:
+                cand = rng.uniform(size=(K, d))
+            else:
+                cand = mean + _unit_ball(rng, K, d) @ B.T
+                cand = cand[((cand > 0.0) & (cand < 1.0)).all(axis=1)]
+            if cand.shape[0]:
+                lc = score(cand)
+                n_evals += cand.shape[0]
+                for k in range(cand.shape[0]):
+                    if st['done']:
+                        break
+                    ea += try_insert(cand[k], float(lc[k]))
+                ep += cand.shape[0]
+            else:
+                ep += 1
+            if ep >= 512:
+                if ea < ep / (1.2 * walks):
+                    mode, sc = 1, 0.3
+                ea = ep = 0
+        else:
+            start = rng.integers(0, nlive, size=K)
+            cu, cl = U[start].copy(), LL[start].copy()
+            moved = np.zeros(K, dtype=bool)
+            lstar = float(LL.min())
+            acc = 0
+            for _ in range(walks):
+                prop = cu + sc * (_unit_ball(rng, K, d) @ B.T)
+                ok = ((prop > 0.0) & (prop < 1.0)).all(axis=1)
+                if ok.any():
+                    lp = np.full(K, -np.inf)
+                    lp[ok] = score(prop[ok])
+                    n_evals += int(ok.sum())
+                    go = ok & (lp > lstar)
+                    cu[go], cl[go] = prop[go], lp[go]
+                    moved |= go
+                    acc += int(go.sum())
+            for k in range(K):
+                if st['done']:
+                    break
+                if moved[k]:
+                    try_insert(cu[k], float(cl[k]))
+            facc = acc / (K * walks)
+            sc = min(max(sc * math.exp((facc - 0.5) / (0.5 * d)), 1e-5), 2.0)
+    # the remaining live points
+    lnw_live = -st['it'] / nlive - math.log(nlive)
+    lnZ, H = st['lnZ'], st['H']
+    for l in LL:
+        lw = float(l) + lnw_live
+        new = _logaddexp(lnZ, lw)
+        if new > -np.inf:
+            t1 = math.exp(lw - new) * float(l) if l > -np.inf else 0.0
+            t2 = math.exp(lnZ - new) * (H + lnZ) if lnZ > -np.inf else 0.0
+            H = t1 + t2 - new
+        lnZ = new
+    return dict(lnZ=lnZ, lnZ_err=math.sqrt(max(H, 0.0) / nlive), max_loglike=st['lmax'], n_iter=st['it'],
+                n_evals=n_evals, n_samples=st['nd'] + nlive)
+
+
+def fit_pixel(xarrs, trans_ids, data, noise, packed_priors, ncomp_max=3, lnZ_thresh=11.0, nlive=100,
+              nlive_snr_fact=5, tol=1.0, efr=0.3, n_prop=32, seed=0):
+    """One pixel through the reference's ncomp escalation (nestfit/main.py:436-472): nlive grows with
+    the peak SNR (main.py:445-447); N -> N + 1 while ln Z_N - ln Z_{N-1} >= lnZ_thresh, starting from the
+    null evidence.  data [n_spec, n_chan], noise [n_spec].  Returns dict(nbest, lnZ[], n_evals)."""
+    from . import oracle as orc
+    data = np.asarray(data, dtype=np.float64)
+    noise = np.asarray(noise, dtype=np.float64)
+    d3, n2 = data[None], noise[None]
+    null = float(-(data * data / (2.0 * noise[:, None] ** 2)).sum())
+    nl = int(nlive + int(nlive_snr_fact * max(float((data.max(axis=1) / noise).max()), 0.0)))
+    lnZ, old, nbest, n_evals = [null], null, 0, 0
+    for ncomp in range(1, ncomp_max + 1):
+        def score(U, ncomp=ncomp):
+            th = orc.prior_transform(packed_priors, U, ncomp)
+            out = orc.nh3_batch(xarrs, trans_ids, np.nan_to_num(th, nan=1.0), ncomp, data=d3, noise=n2)["lnL"]
+            out[~np.isfinite(th).all(axis=1)] = np.nan
+            return out
+        res = nested_sampling(score, 6 * ncomp, nl, tol=tol, efr=efr, n_prop=n_prop, seed=seed + 7919 * ncomp)
+        n_evals += res['n_evals']
+        lnZ.append(res['lnZ'])
+        if res['lnZ'] - old >= lnZ_thresh:
+            old, nbest = res['lnZ'], ncomp
+        else:
+            break
+    return dict(nbest=nbest, lnZ=lnZ, n_evals=n_evals, nlive=nl)

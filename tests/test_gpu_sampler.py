@@ -191,3 +191,41 @@ def test_consecutive_samplers_and_max_loglike_sanity(nb):
         # best-fit vectors are finite physical parameters
         assert np.isfinite(res["bestfit"]).all()
         ns.close()
+
+
+def test_lnz_agrees_with_cpu_port(nb):
+    """The CUDA driver against the independent numpy port of the same scheme (oracle/ns_port.py) scored
+    with the C oracle likelihood, on the same pixel: the evidences agree within their scatter.  (MultiNest
+    is absent: this and the quadrature test are what pins ln Z.)"""
+    from nestfit_b200.sampler import NestedSamplingBatch
+    from oracle import ns_port
+    blk, ut, truth = nh3_problem(nb, 1, n_pix=1, seed=33)
+    xs = [orc.bench_axis(1, 400, 0.158), orc.bench_axis(2, 400, 0.158)]
+    # the pixel nh3_problem uploaded (same seed, same draw order), as the FP32 values the GPU holds
+    clean = orc.nh3_batch(xs, [1, 2], truth[None], 1, want_pred=True)["pred"][0]
+    data = (clean[None] + np.random.default_rng(33).normal(0, 0.1, (1,) + clean.shape)).astype(np.float32)[0]
+    data = data.astype(np.float64)
+    lnl_gpu = blk.loglike(truth[None], 1)[0]
+    lnl_cpu = orc.nh3_batch(xs, [1, 2], truth[None], 1, data=data[None], noise=np.full((1, 2), 0.1))["lnL"][0]
+    assert abs(lnl_gpu - lnl_cpu) < 1e-3 + 2e-6 * abs(lnl_cpu)       # same pixel on both sides
+    packed = ut.pack()
+
+    def score(U):
+        th = orc.prior_transform(packed, U, 1)
+        out = orc.nh3_batch(xs, [1, 2], np.nan_to_num(th, nan=1.0), 1, data=data[None], noise=np.full((1, 2), 0.1))["lnL"]
+        out[~np.isfinite(th).all(axis=1)] = np.nan
+        return out
+    cpu = [ns_port.nested_sampling(score, 6, 200, tol=0.5, seed=s) for s in range(4)]
+    # eight independent GPU runs of the same pixel in one batch (distinct Philox streams per run)
+    ns = NestedSamplingBatch(blk, ut, 1, pix_ids=np.zeros(8, dtype=np.int32), nlive=200, tol=0.5, n_prop=32, seed=5)
+    res = ns.run()
+    ns.close()
+    zc, zg = np.array([c['lnZ'] for c in cpu]), res["lnZ"]
+    err = np.sqrt(np.mean([c['lnZ_err'] for c in cpu]) ** 2 / 4 + np.mean(res["lnZ_err"]) ** 2 / 8)
+    assert abs(zc.mean() - zg.mean()) < 4 * err + 0.1, (zc, zg, err)
+    # the same maximum of the likelihood (FP32 kernel vs FP64 oracle on slightly different best samples)
+    assert abs(max(c['max_loglike'] for c in cpu) - res["max_loglike"].max()) < 1.0
+    # and the same cost per iteration within a factor (same proposal scheme)
+    rc = np.mean([c['n_evals'] / c['n_iter'] for c in cpu])
+    rg = np.mean(res["n_evals"] / res["n_iter"])
+    assert 0.5 < rc / rg < 2.0, (rc, rg)
