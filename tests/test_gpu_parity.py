@@ -251,3 +251,39 @@ def test_full_size_properties(nb):
     # (d) never better than a perfect fit bound and never above 0; best vector per pixel beats null
     null = blk.null_lnZ()
     assert (lnl.reshape(n_pix, vpp).max(axis=1) > null - 1e-6).mean() > 0.5
+
+
+def test_predict_loglike_consistency_properties(nb):
+    """Properties tying the two kernels together, independent of the oracle: (a) a pixel made of the predict
+    kernel's own output is fitted exactly (lnL = 0); (b) lnL equals the chi-square of data - predict summed on the
+    host; (c) a component entirely outside the band changes nothing (ncomp = 3 vs ncomp = 2); (d) exchanging two
+    components leaves lnL unchanged to FP32 round-off."""
+    rng = np.random.default_rng(77)
+    ncomp, n = 3, 2048
+    ut, xs, data, noise = _random_problem(nb, rng, ncomp, 4, 1000, 0.07)
+    P = ut.transform_batch(rng.uniform(size=(n, 18)), ncomp)
+    P = P[np.isfinite(P).all(axis=1)]
+    n = P.shape[0]
+    scratch = nb.PixelBlock("ammonia", xs, data, noise, trans_ids=[1, 2])
+    pred = scratch.predict(P, ncomp)                                   # [n, 2, 1000] float32
+    # (b) against the first four pixels
+    pix = (np.arange(n) % 4).astype(np.int32)
+    lnl = scratch.loglike(P, ncomp, pix_of_vec=pix)
+    d = data[pix].astype(np.float64) - pred.astype(np.float64)
+    want = -(d * d / (2.0 * np.asarray(noise, dtype=np.float64)[pix][:, :, None] ** 2)).sum(axis=(1, 2))
+    np.testing.assert_allclose(lnl, want, rtol=3e-6, atol=1e-3)
+    # (c) third component moved out of the band == two-component model of the first two
+    P3 = P.copy()
+    P3[:, 2] = 900.0                                                   # voff of component 3 [km/s]
+    P2 = np.ascontiguousarray(P.reshape(n, 6, 3)[:, :, :2].reshape(n, 12))
+    np.testing.assert_allclose(scratch.loglike(P3, 3, pix_of_vec=pix), scratch.loglike(P2, 2, pix_of_vec=pix),
+                               rtol=3e-6, atol=1e-3)
+    # (d) components 1 and 2 exchanged
+    Px = P.reshape(n, 6, 3)[:, :, [1, 0, 2]].reshape(n, 18).copy()
+    np.testing.assert_allclose(scratch.loglike(Px, 3, pix_of_vec=pix), lnl, rtol=3e-6, atol=1e-3)
+    scratch.close()
+    # (a) pixels = predicted spectra, one vector per pixel
+    own = nb.PixelBlock("ammonia", xs, pred, 0.1, trans_ids=[1, 2])
+    z = own.loglike(P, ncomp, vecs_per_pix=1)
+    assert np.all(np.abs(z) <= 1e-9), np.abs(z).max()
+    own.close()
