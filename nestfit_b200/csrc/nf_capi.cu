@@ -232,30 +232,35 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
     int rc = ensure_stage(px, total);
     if (rc != NF_OK) return rc;
 
-    cudaEvent_t ev0[2], ev1[2];
-    for (int i = 0; i < 2; ++i) { NF_CUDA(cudaEventCreate(&ev0[i])); NF_CUDA(cudaEventCreate(&ev1[i])); }
+    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
     double kernel_ms = 0.0;
     int64_t launches = 0;
     bool pending[2] = {false, false};
     int status = NF_OK;
+    // errors inside the pipeline leave through `status` so that the events are always destroyed
+#define NF_STEP(expr) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { status = (int)e__; break; } }
+    for (int i = 0; i < 2 && status == NF_OK; ++i) {
+        NF_STEP(cudaEventCreate(&ev0[i]));
+        NF_STEP(cudaEventCreate(&ev1[i]));
+    }
     int64_t k = 0;
     for (int64_t b0 = 0; b0 < B && status == NF_OK; b0 += chunk, ++k) {
         const int slot = (int)(k & 1);
         cudaStream_t st = px->streams[slot];
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
         if (pending[slot]) {   // the slot's previous chunk must have drained its buffers
-            NF_CUDA(cudaStreamSynchronize(st));
+            NF_STEP(cudaStreamSynchronize(st));
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev0[slot], ev1[slot]);
             kernel_ms += ms;
             pending[slot] = false;
         }
         unsigned char *dev = (unsigned char *)px->stage_dev[slot];
-        NF_CUDA(cudaMemcpyAsync(dev, (const unsigned char *)params_host + (size_t)b0 * ndim * psz,
+        NF_STEP(cudaMemcpyAsync(dev, (const unsigned char *)params_host + (size_t)b0 * ndim * psz,
                                 (size_t)nb * ndim * psz, cudaMemcpyHostToDevice, st));
         const int32_t *pix_dev = nullptr;
         if (pix_host) {
-            NF_CUDA(cudaMemcpyAsync(dev + off_pix, pix_host + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+            NF_STEP(cudaMemcpyAsync(dev + off_pix, pix_host + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
             pix_dev = (const int32_t *)(dev + off_pix);
         }
         NfLikeArgs a;
@@ -269,18 +274,18 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
             a.inv2s2 = px->inv2s2 + (b0 / a.vecs_per_pix) * px->n_spec;
             a.d2chunk = px->d2chunk + (b0 / a.vecs_per_pix) * px->n_spec * (px->n_pad / 32);
         }
-        NF_CUDA(cudaEventRecord(ev0[slot], st));
-        cudaError_t e = launch_model(model, a, st);
-        if (e != cudaSuccess) { status = (int)e; break; }
-        NF_CUDA(cudaEventRecord(ev1[slot], st));
+        NF_STEP(cudaEventRecord(ev0[slot], st));
+        NF_STEP(launch_model(model, a, st));
+        NF_STEP(cudaEventRecord(ev1[slot], st));
         ++launches;
-        if (lnL_host)
-            NF_CUDA(cudaMemcpyAsync(lnL_host + b0, dev + off_lnl, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
-        if (want_pred)
-            NF_CUDA(cudaMemcpyAsync((unsigned char *)pred_host + (size_t)b0 * pred_per_vec, dev + off_pred,
-                                    (size_t)nb * pred_per_vec, cudaMemcpyDeviceToHost, st));
         pending[slot] = true;
+        if (lnL_host)
+            NF_STEP(cudaMemcpyAsync(lnL_host + b0, dev + off_lnl, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        if (want_pred)
+            NF_STEP(cudaMemcpyAsync((unsigned char *)pred_host + (size_t)b0 * pred_per_vec, dev + off_pred,
+                                    (size_t)nb * pred_per_vec, cudaMemcpyDeviceToHost, st));
     }
+#undef NF_STEP
     for (int slot = 0; slot < 2; ++slot) {
         cudaError_t e = cudaStreamSynchronize(px->streams[slot]);
         if (e != cudaSuccess && status == NF_OK) status = (int)e;
@@ -290,7 +295,10 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
             kernel_ms += ms;
         }
     }
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
+    for (int i = 0; i < 2; ++i) {
+        if (ev0[i]) cudaEventDestroy(ev0[i]);
+        if (ev1[i]) cudaEventDestroy(ev1[i]);
+    }
     g_nf_last_kernel_ms = kernel_ms;
     g_nf_last_launches = launches;
     return status;
