@@ -413,27 +413,49 @@ class CubeFitter:
             return res
         return self.fit_block((all_lon, all_lat), device=device)
 
-    def fit_cube(self, store_name='run/test_cube', nproc=1, timeout=None):
-        """Fit every pixel and write the store.  `nproc` = number of GPUs (one process
-        per GPU, contiguous pixel blocks, one chunk file per process)."""
+    def fit_cube(self, store_name='run/test_cube', nproc=1, timeout=None, blocks_per_gpu=1, devices=None):
+        """Fit every pixel and write the store.  `nproc` = number of GPUs: one process per GPU, one chunk
+        file per process (main.py:476-526).  With `blocks_per_gpu` = 1 every process fits one contiguous pixel
+        block; with more, the cube is cut into `nproc * blocks_per_gpu` contiguous blocks that the processes
+        take from a shared queue as they finish (pixels differ in cost: nlive grows with the SNR and the
+        number of model runs with the number of components).  `devices` lists the CUDA device
+        of each process (default 0 .. nproc-1)."""
         n_lon = self.stack.spatial_shape[0]
         if nproc > n_lon:
             raise ValueError(f'The pixel width of the image in longitude ({n_lon}) ' +
                              f'must be greater than or equal to the number of processes ({nproc}).')
+        if blocks_per_gpu < 1:
+            raise ValueError(f'blocks_per_gpu must be positive: {blocks_per_gpu}')
+        devices = list(range(nproc)) if devices is None else [int(d) for d in devices]
+        if len(devices) != nproc:
+            raise ValueError(f'devices must name one CUDA device per process: {devices}')
         store = HdfStore(store_name, nchunks=nproc)
         store.insert_header(self.stack)
         store.insert_fitter_pars(self)
         store.insert_model_metadata(self.runner_cls)
-        indices = get_block_indices(self.stack.spatial_shape, store.nchunks)
+        n_blocks = store.nchunks * int(blocks_per_gpu)
+        n_pix = int(np.prod(self.stack.spatial_shape))
+        indices = get_block_indices(self.stack.spatial_shape, min(n_blocks, n_pix))
         self._store = store
         results = []
         if store.nchunks == 1:
-            self._device = 0
-            results.append(self.fit(indices[0], store.chunk_paths[0]))
+            self._device = devices[0]
+            lon = np.concatenate([b[0] for b in indices])
+            lat = np.concatenate([b[1] for b in indices])
+            results.append(self.fit((lon, lat), store.chunk_paths[0]))
         else:
             import multiprocessing as mp
             ctx = mp.get_context('spawn')
-            procs = [ctx.Process(target=_fit_worker, args=(self, i, indices[i], str(store.chunk_paths[i])))
+            queue = None
+            if blocks_per_gpu > 1:
+                queue = ctx.Queue()
+                for j in range(len(indices)):
+                    queue.put(j)
+                for _ in range(store.nchunks):
+                    queue.put(None)                 # one stop mark per process
+            procs = [ctx.Process(target=_fit_worker,
+                                 args=(self, i, devices[i], indices if queue is not None else indices[i],
+                                       str(store.chunk_paths[i]), queue))
                      for i in range(store.nchunks)]
             for proc in procs:
                 proc.start()
@@ -448,8 +470,9 @@ class CubeFitter:
         return results
 
 
-def _fit_worker(fitter, i, indices, chunk_path):
-    fitter._device = i
+def _fit_worker(fitter, i, device, indices, chunk_path, queue=None):
+    """Process `i` of fit_cube: fits its block (or blocks taken from `queue`) on `device` into chunk `i`."""
+    fitter._device = device
     fitter._store = HdfStore.__new__(HdfStore)
     # lightweight re-attachment to the already created store directory
     from pathlib import Path
@@ -459,4 +482,15 @@ def _fit_worker(fitter, i, indices, chunk_path):
     store._open = True
     store.hdf = None
     os.environ.setdefault('HDF5_USE_FILE_LOCKING', 'FALSE')
-    fitter.fit(indices, store.chunk_paths[i])
+    if queue is None:
+        fitter.fit(indices, store.chunk_paths[i])
+        return
+    root = store.open_chunk(i)
+    try:
+        while True:
+            j = queue.get()
+            if j is None:
+                break
+            fitter.fit_block(indices[j], device=device, group_root=root)
+    finally:
+        store.close_chunk(i, root)

@@ -53,14 +53,8 @@ def test_fit_cube_small(nb, tmp_path):
     store.close()
 
 
-def test_fit_cube_two_gpus(nb, tmp_path):
-    """fit_cube(nproc=2): one spawned process per GPU, contiguous pixel blocks, one chunk file each,
-    linked into the table (main.py:476-526, 313-322).  Skipped on single-GPU boxes."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+def _two_block_problem(nb):
     from nestfit_b200.synth import make_synth_stack
-    from nestfit_b200.store import HdfStore
     from nestfit_b200.models import ammonia
     ut = nb.get_irdc_priors()
     ncomp_map = np.zeros((4, 4), dtype=int)
@@ -70,12 +64,16 @@ def test_fit_cube_two_gpus(nb, tmp_path):
                         trans_ids=[1, 2])
     t1 = np.array([[0.3, 14.0, 6.0, 14.6, 0.45, 0.0]])
     clean = blk.predict(t1, 1)[0]
+    blk.close()
     rng = np.random.default_rng(8)
     for c in (0, 1):
         stack.cubes[c].data[2:] = clean[c] + rng.normal(0, 0.1, (2, 4, 400))
-    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 100}, seed=6)
-    fitter.fit_cube(str(tmp_path / 'cube2'), nproc=2)
-    store = HdfStore(str(tmp_path / 'cube2'))
+    return nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 100}, seed=6)
+
+
+def _check_two_block_store(path):
+    from nestfit_b200.store import HdfStore
+    store = HdfStore(path)
     assert store.nchunks == 2 and all(p.exists() for p in store.chunk_paths)
     groups = list(store.iter_pix_groups())
     assert len(groups) == 16
@@ -84,3 +82,25 @@ def test_fit_cube_two_gpus(nb, tmp_path):
         nbest[g.attrs['i_lon'], g.attrs['i_lat']] = g.attrs['nbest']
     assert np.all(nbest[:2] == 0) and np.all(nbest[2:] == 1)
     store.close()
+
+
+def test_fit_cube_two_gpus(nb, tmp_path):
+    """fit_cube(nproc=2): one spawned process per GPU, contiguous pixel blocks, one chunk file each,
+    linked into the table (main.py:476-526, 313-322).  Skipped on single-GPU boxes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fitter = _two_block_problem(nb)
+    fitter.fit_cube(str(tmp_path / 'cube2'), nproc=2)
+    _check_two_block_store(str(tmp_path / 'cube2'))
+
+
+def test_fit_cube_dynamic_blocks(nb, tmp_path):
+    """fit_cube(nproc=2, blocks_per_gpu=3): six contiguous blocks handed out from a queue to two worker
+    processes (both on device 0 here so that the test also runs on a single-GPU box); every pixel is fitted
+    exactly once and lands in the chunk of the process that took its block."""
+    fitter = _two_block_problem(nb)
+    fitter.fit_cube(str(tmp_path / 'cube3'), nproc=2, blocks_per_gpu=3, devices=[0, 0])
+    _check_two_block_store(str(tmp_path / 'cube3'))
+    with pytest.raises(ValueError):
+        fitter.fit_cube(str(tmp_path / 'cube4'), nproc=2, devices=[0])
