@@ -108,7 +108,8 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     px->n_pix = n_pix;
     px->n_spec = n_spec;
     px->n_chan = n_chan;
-    px->n_pad = ((n_chan + 63) / 64) * 64;      // the hyperfine kernel walks 64-channel chunks
+    // the hyperfine kernel walks 64-channel chunks, the Gaussian kernel 128-channel chunks
+    px->n_pad = model == NF_MODEL_GAUSS ? ((n_chan + 127) / 128) * 128 : ((n_chan + 63) / 64) * 64;
     int rc = fill_meta(px, nu_min, nu_chan, trans_id, rest_freq);
     if (rc != NF_OK) { delete px; return rc; }
     cudaError_t e;

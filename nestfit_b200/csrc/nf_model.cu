@@ -3,8 +3,9 @@
 //
 // One warp scores one parameter vector against one pixel:
 //   lanes <-> components during the FP64 set-up (window with the reference's floor rule),
-//   lanes <-> channels during the FP32 main loop: 64-channel chunks, lane l owns channels 64 g + l
-//   and 64 g + l + 32 (packed FP32x2 across the two channels).
+//   lanes <-> channels during the FP32 main loop: 128-channel chunks, lane l owns channels 128 g + l
+//   + {0, 32, 64, 96} (packed FP32x2 across channel pairs): most chunks are touched by one component, so
+//   four channels per lane spread the per-chunk work (ballot, bit walk, residual) over more terms.
 // A CTA (8 warps) works on a tile of consecutive vectors; the pixel of the tile's first vector
 // is staged once in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).  Components
 // are unordered and have unequal widths, so the components touching a chunk are found by ballot;
@@ -86,7 +87,7 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
 
     const int ncomp = a.ncomp;
     const int ndim = 3 * ncomp;
-    const int nchunks = (a.n_chan + 63) >> 6;        // 64-channel chunks (rows are padded to a multiple of 64)
+    const int nchunks = (a.n_chan + 127) >> 7;       // 128-channel chunks (rows are padded to a multiple of 128)
     const NfSpecMeta &sm = a.spec[0];
     const double nu_min = sm.nu_min, inv_chan = sm.inv_chan, f0 = sm.nu0;
     const float lane_f = (float)lane;
@@ -145,7 +146,7 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
             // chunks [sb, sb+32) touched by this lane's component, and by any component
             uint32_t cm = 0u;
             {
-                int c_lo = (lo >> 6) - sb, c_hi = ((hi - 1) >> 6) - sb;
+                int c_lo = (lo >> 7) - sb, c_hi = ((hi - 1) >> 7) - sb;
                 if (on && c_hi >= 0 && c_lo < 32) {
                     c_lo = max(c_lo, 0);
                     c_hi = min(c_hi, 31);
@@ -156,49 +157,66 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
             if (have_data) {          // a chunk no component touches contributes its sum of d^2
                 const int g = sb + lane;
                 if (g < nchunks && !((un >> lane) & 1u)) {
-                    const float2 q = __ldg(reinterpret_cast<const float2 *>(a.d2chunk + pix * (int64_t)(a.n_pad >> 5)) + g);
-                    acc += q.x + q.y;
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(a.d2chunk + pix * (int64_t)(a.n_pad >> 5)) + g);
+                    acc += (q.x + q.y) + (q.z + q.w);
                 }
             }
             while (un) {
                 const int cc = __ffs(un) - 1;
                 un &= un - 1;
                 uint32_t lm = __ballot_sync(NF_FULL, (cm >> cc) & 1u);
-                const int j0 = (sb + cc) << 6;
+                const int j0 = (sb + cc) << 7;
                 const float xa = (float)j0 + lane_f;
-                const uint64_t x2 = pack2(xa, xa + 32.0f);
-                float ma = 0.0f, mb = 0.0f;
+                const uint64_t x2a = pack2(xa, xa + 32.0f), x2b = pack2(xa + 64.0f, xa + 96.0f);
+                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                 while (lm) {          // components are unordered: walk the set bits
                     const int i = __ffs(lm) - 1;
                     lm &= lm - 1;
                     const uint32_t ra = rec_addr + (uint32_t)i * (uint32_t)sizeof(GaussRec);
                     const float4 A = gauss_lds128(ra);
                     const float h = gauss_lds_f32(ra + 16);
-                    const uint64_t d2 = add2(x2, pack2(A.x, A.x));             // exact: multiples of 1/2
-                    const uint64_t t2 = fma2(pack2(A.y, A.y), d2, pack2(A.z, A.z));
-                    float da, db, ea, eb;
-                    unpack2(d2, da, db);
-                    unpack2(mul2(t2, d2), ea, eb);      // -k2 (d^2 - 2 phi' d) log2(e); 2^(-k2 phi'^2) is in A.w
-                    ea = ex2_approx(ea);
-                    eb = ex2_approx(eb);
-                    if (fabsf(da) <= h) ma = fmaf(A.w, ea, ma);
-                    if (fabsf(db) <= h) mb = fmaf(A.w, eb, mb);
+                    const uint64_t R2 = pack2(A.x, A.x), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z);
+                    const uint64_t da2 = add2(x2a, R2), db2 = add2(x2b, R2);       // exact: multiples of 1/2
+                    const uint64_t ta2 = fma2(K2, da2, B2), tb2 = fma2(K2, db2, B2);
+                    float d0, d1, d2, d3, e0, e1, e2, e3;
+                    unpack2(da2, d0, d1);
+                    unpack2(db2, d2, d3);
+                    unpack2(mul2(ta2, da2), e0, e1);    // -k2 (d^2 - 2 phi' d) log2(e); 2^(-k2 phi'^2) is in A.w
+                    unpack2(mul2(tb2, db2), e2, e3);
+                    e0 = ex2_approx(e0);
+                    e1 = ex2_approx(e1);
+                    e2 = ex2_approx(e2);
+                    e3 = ex2_approx(e3);
+                    if (fabsf(d0) <= h) m0 = fmaf(A.w, e0, m0);
+                    if (fabsf(d1) <= h) m1 = fmaf(A.w, e1, m1);
+                    if (fabsf(d2) <= h) m2 = fmaf(A.w, e2, m2);
+                    if (fabsf(d3) <= h) m3 = fmaf(A.w, e3, m3);
                 }
                 if (WRITE_PRED) {
-                    if (j0 + lane < a.n_chan) prow[j0 + lane] = ma;
-                    if (j0 + lane + 32 < a.n_chan) prow[j0 + lane + 32] = mb;
+                    const int j = j0 + lane;
+                    if (j < a.n_chan) prow[j] = m0;
+                    if (j + 32 < a.n_chan) prow[j + 32] = m1;
+                    if (j + 64 < a.n_chan) prow[j + 64] = m2;
+                    if (j + 96 < a.n_chan) prow[j + 96] = m3;
                 } else {
-                    float da, db;
+                    float q0, q1, q2, q3;
                     if (staged) {
-                        da = gauss_lds_f32(srow + (uint32_t)j0 * 4u);
-                        db = gauss_lds_f32(srow + (uint32_t)j0 * 4u + 128u);
+                        const uint32_t sa = srow + (uint32_t)j0 * 4u;
+                        q0 = gauss_lds_f32(sa);
+                        q1 = gauss_lds_f32(sa + 128u);
+                        q2 = gauss_lds_f32(sa + 256u);
+                        q3 = gauss_lds_f32(sa + 384u);
                     } else {
-                        da = __ldg(grow + j0);
-                        db = __ldg(grow + j0 + 32);
+                        q0 = __ldg(grow + j0);
+                        q1 = __ldg(grow + j0 + 32);
+                        q2 = __ldg(grow + j0 + 64);
+                        q3 = __ldg(grow + j0 + 96);
                     }
-                    const float ra_ = da - ma, rb_ = db - mb;
-                    acc = fmaf(ra_, ra_, acc);
-                    acc = fmaf(rb_, rb_, acc);
+                    q0 -= m0; q1 -= m1; q2 -= m2; q3 -= m3;
+                    acc = fmaf(q0, q0, acc);
+                    acc = fmaf(q1, q1, acc);
+                    acc = fmaf(q2, q2, acc);
+                    acc = fmaf(q3, q3, acc);
                 }
             }
         }
