@@ -474,6 +474,13 @@ def _cube_cpu_worker(ix):
     return r["nbest"], r["n_evals"], time.perf_counter() - t0
 
 
+CUBE_CPU_CAP_S = 180.0      # wall-time cap of the cube-fit CPU baseline: keeps the default run within a few minutes
+
+
+def _cube_cpu_worker_ix(ix):
+    return ix, _cube_cpu_worker(ix)
+
+
 def cube_cpu_baseline(stack, ut, shape, nbest_gpu):
     """CPU baseline of the cube-fit metric: the same batched nested-sampling scheme and ncomp
     escalation as a numpy port (oracle/ns_port.py) scored with the C oracle likelihood, one pixel per host core
@@ -488,16 +495,31 @@ def cube_cpu_baseline(stack, ut, shape, nbest_gpu):
     _W["cube"] = ([np.asarray(c.xarr, dtype=np.float64) for c in stack.cubes], ut.pack(),
                   np.asarray(data, dtype=np.float64), np.asarray(noise, dtype=np.float64))
     t0 = time.perf_counter()
+    res, done_ix = [], []
+    cap_s = CUBE_CPU_CAP_S
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cube_cpu_worker, range(cores), chunksize=1)
+        it = pool.imap_unordered(_cube_cpu_worker_ix, range(cores), chunksize=1)
+        try:
+            for _ in range(cores):
+                ix, r = it.next(timeout=max(1.0, cap_s - (time.perf_counter() - t0)))
+                done_ix.append(ix)
+                res.append(r)
+        except mp.TimeoutError:
+            pool.terminate()          # the most expensive pixels did not finish within the cap
     wall = time.perf_counter() - t0
+    if not res:
+        return {"value": None, "unit": "pixels/s", "cores": cores, "kind": "port",
+                "sample": f"no pixel finished within {cap_s:.0f} s"}
+    lon, lat = lon[done_ix], lat[done_ix]
     nb_cpu = np.array([r[0] for r in res])
     # throughput of a cube of many such pixels with every core kept busy (the wall time of this small sample is
     # set by its slowest pixel and would understate the CPU)
-    busy = float(np.sum([r[2] for r in res]))
+    # (pixels cut off by the wall-time cap count with the core time they used up but not as fitted pixels)
+    busy = float(np.sum([r[2] for r in res])) + (cores - len(res)) * wall
     return {"value": len(res) * cores / busy, "unit": "pixels/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} pixels spread over the cube, one per core (numpy port of the sampler + C oracle "
-                      "likelihood, same nlive/tol/efr/escalation)",
+            "truncated": len(res) < cores,
+            "sample": f"{len(res)} of {cores} pixels spread over the cube, one per core (numpy port of the sampler + C "
+                      "oracle likelihood, same nlive/tol/efr/escalation)",
             "wall_seconds": wall, "likelihood_evals_per_pixel": float(np.mean([r[1] for r in res])),
             "cpu_seconds_per_pixel": float(np.mean([r[2] for r in res])),
             "nbest_agrees_with_gpu": float((nb_cpu == nbest_gpu[lon, lat]).mean())}
