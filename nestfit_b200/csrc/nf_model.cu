@@ -53,6 +53,21 @@ __device__ __forceinline__ float4 gauss_lds128(uint32_t addr)
     return v;
 }
 
+// Index of the lowest set bit without FLO/BREV (they execute on the XU pipe, which the exponentials need):
+// de Bruijn multiplication, table in constant memory, scaled by sizeof(GaussRec).
+__constant__ uint32_t g_lsb_rec_off[32] = {
+    0 * 32, 1 * 32, 28 * 32, 2 * 32, 29 * 32, 14 * 32, 24 * 32, 3 * 32, 30 * 32, 22 * 32, 20 * 32, 15 * 32, 25 * 32,
+    17 * 32, 4 * 32, 8 * 32, 31 * 32, 27 * 32, 13 * 32, 23 * 32, 21 * 32, 19 * 32, 16 * 32, 7 * 32, 26 * 32, 12 * 32,
+    18 * 32, 6 * 32, 11 * 32, 5 * 32, 10 * 32, 9 * 32};
+static_assert(sizeof(GaussRec) == 32, "g_lsb_rec_off is scaled by the record size");
+
+// Four channels of a pixel row that is not the CTA's staged pixel (rare: tiles straddling two pixels).  Kept out
+// of line so that the compiler does not predicate these loads into the common path.
+__device__ __noinline__ float4 gauss_row4_global(const float *p)
+{
+    return make_float4(__ldg(p), __ldg(p + 32), __ldg(p + 64), __ldg(p + 96));
+}
+
 // WRITE_PRED = false: log-likelihood against the pixel's data (a.data, a.lnL);
 // WRITE_PRED = true : model spectra only (a.pred), no data are read.
 template <bool WRITE_PRED, typename PT>
@@ -161,18 +176,20 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
                     acc += (q.x + q.y) + (q.z + q.w);
                 }
             }
-            while (un) {
-                const int cc = __ffs(un) - 1;
-                un &= un - 1;
+            // touched chunks in ascending order: windows are wide, so nearly every chunk between the first
+            // and the last touched one is visited and a plain scan beats a find-first-set walk
+            int cc = un ? __ffs(un) - 1 : 32;
+            float xa = (float)((sb + cc) << 7) + lane_f;
+            for (uint32_t rest = un >> (cc & 31); cc < 32 && rest; ++cc, rest >>= 1, xa += 128.0f) {
+                if (!(rest & 1u)) continue;
                 uint32_t lm = __ballot_sync(NF_FULL, (cm >> cc) & 1u);
                 const int j0 = (sb + cc) << 7;
-                const float xa = (float)j0 + lane_f;
                 const uint64_t x2a = pack2(xa, xa + 32.0f), x2b = pack2(xa + 64.0f, xa + 96.0f);
                 float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                 while (lm) {          // components are unordered: walk the set bits
-                    const int i = __ffs(lm) - 1;
-                    lm &= lm - 1;
-                    const uint32_t ra = rec_addr + (uint32_t)i * (uint32_t)sizeof(GaussRec);
+                    const uint32_t lsb = lm & (0u - lm);
+                    lm ^= lsb;
+                    const uint32_t ra = rec_addr + g_lsb_rec_off[(lsb * 0x077CB531u) >> 27];
                     const float4 A = gauss_lds128(ra);
                     const float h = gauss_lds_f32(ra + 16);
                     const uint64_t R2 = pack2(A.x, A.x), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z);
@@ -207,10 +224,8 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
                         q2 = gauss_lds_f32(sa + 256u);
                         q3 = gauss_lds_f32(sa + 384u);
                     } else {
-                        q0 = __ldg(grow + j0);
-                        q1 = __ldg(grow + j0 + 32);
-                        q2 = __ldg(grow + j0 + 64);
-                        q3 = __ldg(grow + j0 + 96);
+                        const float4 q = gauss_row4_global(grow + j0);
+                        q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
                     }
                     q0 -= m0; q1 -= m1; q2 -= m2; q3 -= m3;
                     acc = fmaf(q0, q0, acc);
