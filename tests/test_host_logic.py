@@ -144,3 +144,19 @@ def test_cubefitter_pickles_for_spawned_workers(nb):
         ut._handles = {}
     assert clone.utrans._handles == {} and clone.utrans.n_param == 6 and clone.ncomp_max == 2
     assert clone.stack.cubes[1].trans_id == 2
+
+
+def test_fit_cube_argument_checks():
+    """fit_cube validates its partitioning arguments before touching a device (main.py:476-486)."""
+    import nestfit_b200 as nb
+    from nestfit_b200.models import ammonia
+
+    class _Stack:
+        spatial_shape = (3, 5)
+    fitter = nb.CubeFitter(_Stack(), None, ammonia.AmmoniaRunner)
+    with pytest.raises(ValueError, match='number of processes'):
+        fitter.fit_cube('unused', nproc=4)
+    with pytest.raises(ValueError, match='blocks_per_gpu'):
+        fitter.fit_cube('unused', nproc=2, blocks_per_gpu=0)
+    with pytest.raises(ValueError, match='one CUDA device per process'):
+        fitter.fit_cube('unused', nproc=2, devices=[0])

@@ -31,3 +31,24 @@ def test_port_rejects_nan_scores():
     r = ns_port.nested_sampling(score, 2, 100, tol=0.5, seed=4)
     truth = math.log(2 * math.pi * 0.01) + math.log(0.5 * (1 + math.erf(0.3 / 0.1 / math.sqrt(2))))
     assert abs(r['lnZ'] - truth) < 4 * r['lnZ_err'] + 0.05
+
+
+def test_fit_pixel_escalation_small():
+    """ncomp escalation of the port (main.py:450-469) on a small two-spectrum pixel: a strong single line is
+    selected as one component, pure noise as none."""
+    import nestfit_b200 as nb
+    from oracle import oracle as orc
+    ut = nb.get_irdc_priors()
+    packed = ut.pack()
+    xs = [orc.bench_axis(1, 160, 0.4), orc.bench_axis(2, 160, 0.4)]
+    rng = np.random.default_rng(12)
+    truth = np.array([[0.4, 14.0, 6.0, 14.6, 0.45, 0.0]])
+    clean = orc.nh3_batch(xs, [1, 2], truth, 1, want_pred=True)["pred"][0]
+    noise = np.array([0.1, 0.1])
+    line = ns_port.fit_pixel(xs, [1, 2], clean + rng.normal(0, 0.1, clean.shape), noise, packed, ncomp_max=2,
+                             nlive=60, nlive_snr_fact=1, seed=3)
+    assert line["nbest"] == 1 and len(line["lnZ"]) == 3
+    assert line["lnZ"][1] - line["lnZ"][0] > 11 and line["lnZ"][2] - line["lnZ"][1] < 11
+    empty = ns_port.fit_pixel(xs, [1, 2], rng.normal(0, 0.1, clean.shape), noise, packed, ncomp_max=2,
+                              nlive=60, nlive_snr_fact=1, seed=4)
+    assert empty["nbest"] == 0 and len(empty["lnZ"]) == 2          # the escalation stops after the failed N = 1
