@@ -459,10 +459,16 @@ class CubeFitter:
                      for i in range(store.nchunks)]
             for proc in procs:
                 proc.start()
+            failed = None
             for proc in procs:
                 proc.join(timeout)
-                if proc.exitcode not in (0, None):
-                    raise RuntimeError(f'GPU worker failed with exit code {proc.exitcode}')
+                if proc.exitcode not in (0, None) and failed is None:
+                    failed = proc.exitcode
+            if failed is not None:
+                for proc in procs:          # do not leave the other workers running behind the error
+                    if proc.is_alive():
+                        proc.terminate()
+                raise RuntimeError(f'GPU worker failed with exit code {failed}')
         store.link_files()
         store.close()
         self._store = None
