@@ -134,7 +134,7 @@ class NestedSamplingBatch:
         null_aic = 2 * k - 2 * nullL
         attrs = {
             'ncomp': self.ncomp, 'null_lnZ': nullL, 'n_chan_tot': int(n_chan_tot),
-            'n_samples': int(res["n_samples"][run]), 'n_live': int(self.nlive[run]), 'n_params': self.ndim,
+            'n_samples': int(post.shape[0]), 'n_live': int(self.nlive[run]), 'n_params': self.ndim,
             'global_lnZ': float(res["lnZ"][run]), 'global_lnZ_err': float(res["lnZ_err"][run]),
             'max_loglike': maxL, 'marg_cols': MARG_COLS, 'marg_quantiles': MARG_QUANTILES,
             'BIC': np.log(n) * k - 2 * maxL, 'AIC': aic, 'AICc': aic + (2 * k**2 + 2 * k) / (n - k - 1),
