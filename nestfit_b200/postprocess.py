@@ -1,5 +1,5 @@
-"""Store post-processing on the predict kernel: host mirror of the aggregation
-steps the reference runs after a cube fit (nestfit/main.py:664-1061) and, batched
+"""Store post-processing on the predict kernel: host mirror of the aggregation and
+convolution steps the reference runs after a cube fit (nestfit/main.py:529-1061) and, batched
 on the GPU, of its two per-pixel ``runner.predict`` loops
 
     deblend_hf_intensity          nestfit/main.py:1064-1133
@@ -110,6 +110,171 @@ def convolve_evidence(store, kernel):
     conv_nbest[overshot] = nbest[overshot] + 1
     store.create_dataset('conv_nbest', conv_nbest, group=dpath)
     store.create_dataset('conv_evidence', cdata, group=dpath)
+
+
+def take_by_components(data, comps, axis=0, incl_zero=True):
+    """Pick, per map position, the entry of `data` (..., b, l) along `axis` that belongs to the number of
+    components in `comps` (b, l): index `comps - 1`, i.e. 1 component -> entry 0 (main.py:529-562).
+    Positions without data (`comps` = -1) and, unless `incl_zero`, noise-only positions (`comps` = 0)
+    become NaN."""
+    comps = np.asarray(comps)
+    idx = np.clip(comps - 1, 0, None)
+    idx = idx.reshape((1,) * (data.ndim - idx.ndim) + idx.shape)
+    out = np.squeeze(np.take_along_axis(data, idx, axis=axis), axis=axis).astype(float, copy=True)
+    out[..., comps < (0 if incl_zero else 1)] = np.nan
+    return out
+
+
+def _circle_rect_area(x0, x1, y0, y1, r):
+    """Exact area of the disc x^2 + y^2 <= r^2 inside the rectangle [x0, x1] x [y0, y1]: the chord
+    y = +-sqrt(r^2 - x^2) clipped to [y0, y1] is integrated piecewise (Gauss-Legendre on the smooth pieces
+    between the abscissae where the chord meets a rectangle edge)."""
+    lo, hi = max(x0, -r), min(x1, r)
+    if hi <= lo:
+        return 0.0
+    cuts = {lo, hi}
+    for y in (y0, y1):
+        if abs(y) < r:
+            c = np.sqrt(r * r - y * y)
+            cuts.update(v for v in (-c, c) if lo < v < hi)
+    cuts = sorted(cuts)
+    gx, gw = np.polynomial.legendre.leggauss(48)
+    area = 0.0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        # substitution x = r sin(t) removes the square-root end-point singularity at |x| = r
+        ta, tb = np.arcsin(np.clip(a / r, -1, 1)), np.arcsin(np.clip(b / r, -1, 1))
+        t = 0.5 * (tb - ta) * gx + 0.5 * (tb + ta)
+        half = r * np.cos(t)
+        seg = np.clip(half, y0, y1) - np.clip(-half, y0, y1)
+        area += 0.5 * (tb - ta) * np.sum(gw * seg * r * np.cos(t))
+    return float(area)
+
+
+def apply_circular_mask(kernel, radius=None):
+    """Weight an odd-shaped kernel by the exact fraction of each pixel inside a circular aperture of
+    `radius` pixels about the centre of the middle pixel (main.py:574-610; the reference takes the overlap
+    grid from photutils, here it is integrated directly)."""
+    kernel = np.asarray(kernel, dtype=float)
+    nx, ny = kernel.shape
+    if radius is None:
+        radius = min(nx, ny) / 2
+    if radius > np.sqrt((nx / 2)**2 + (ny / 2)**2):
+        return kernel
+    if nx % 2 == 0 or ny % 2 == 0:
+        raise ValueError(f'Kernel dimensions must be odd: ({nx}, {ny})')
+    weights = np.empty((nx, ny))
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0 = i - nx / 2, j - ny / 2
+            weights[i, j] = _circle_rect_area(x0, x0 + 1, y0, y0 + 1, radius)
+    return weights * kernel
+
+
+def get_indep_info_kernel(sigma, nrad=1, sigma_taper=None):
+    """(2 nrad + 1)^2 kernel of the information that is independent of the centre pixel for a symmetric
+    Gaussian beam of standard deviation `sigma` pixels: one minus the beam integrated over each pixel
+    relative to its peak, per beam area; optional Gaussian taper; centre = 1 (main.py:613-661)."""
+    from math import erf
+    assert isinstance(nrad, int) and nrad >= 0
+    if nrad == 0:
+        return np.array([[1.0]])
+    ppbeam = max(1.0, 2 * np.pi * sigma**2)            # a beam smaller than a pixel still counts as one
+    ax = np.arange(-nrad, nrad + 1, dtype=float)
+    cdf = np.vectorize(lambda z: 0.5 * (1 + erf(z / sigma / np.sqrt(2))))
+    frac = cdf(ax + 0.5) - cdf(ax - 0.5)               # beam fraction inside each pixel column / row
+    kernel = (1 - np.outer(frac, frac) * (2 * np.pi * sigma**2)) / ppbeam
+    if sigma_taper is not None:
+        kernel = kernel * np.exp(-0.5 * (ax[:, None]**2 + ax[None, :]**2) / sigma_taper**2)
+    kernel[nrad, nrad] = 1
+    return kernel
+
+
+def _as_kernel(kernel):
+    if isinstance(kernel, (int, float)):
+        kernel = gaussian_kernel2d(float(kernel))
+    return np.asarray(kernel, dtype=np.float64)
+
+
+def extended_masked_evidence(store, kernel, conv=True, lnz_thresh=3):
+    """'mext_evidence' (b, l): evidence difference of the one-component model after masking the positions
+    already detected above `lnz_thresh` and convolving with `kernel`, to bring out weak extended emission
+    (main.py:777-816)."""
+    kernel = _as_kernel(kernel)
+    hdf, dpath = store.hdf, store.dpath
+    data = np.array(hdf[f'{dpath}/evidence'][...], dtype=float)
+    mdata = np.asarray(hdf[f"{dpath}/{'conv_evidence' if conv else 'evidence'}"][...])
+    mdata = mdata[1] - mdata[0]
+    with np.errstate(invalid='ignore'):
+        mask = mdata > lnz_thresh
+    cdata = nans(data.shape)
+    for i in range(data.shape[0]):
+        data[i, mask] = np.nan
+        cdata[i] = convolve_nan_extend(data[i], kernel)
+    mext = cdata[1] - cdata[0]
+    mext[np.isnan(mdata) | mask] = np.nan
+    store.create_dataset('mext_evidence', mext, group=dpath)
+
+
+def convolve_fill_interp(data, kernel):
+    """Convolution of the last two axes of `data` with zero fill outside the map, NaNs interpolated over by
+    renormalising the kernel on the valid pixels, and the kernel's own sum kept (not normalised) -- the
+    semantics of ``astropy.convolution.convolve_fft(x, kernel, normalize_kernel=False)`` that
+    `convolve_post_pdfs` relies on (main.py:1008-1009)."""
+    from scipy import ndimage
+    kernel = np.asarray(kernel, dtype=np.float64)
+    scale = kernel.sum()
+    k = (kernel / scale).reshape((1,) * (data.ndim - 2) + kernel.shape)
+    good = np.isfinite(data)
+    num = ndimage.convolve(np.where(good, data, 0.0), k, mode='constant', cval=0.0)
+    wt = ndimage.convolve(good.astype(np.float64), k, mode='constant', cval=1.0)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        out = num / wt * scale
+    out[wt <= 0] = np.nan
+    return out
+
+
+def convolve_post_pdfs(store, kernel, evid_weight=True):
+    """'conv_post_pdfs' (r, m, p, h, b, l): the posterior PDFs multiplied over neighbouring pixels, i.e.
+    their logarithms convolved with `kernel`, optionally weighted by each pixel's evidence over the null
+    model scaled to [0, 1]; renormalised over the histogram axis (main.py:956-1017)."""
+    kernel = _as_kernel(kernel)
+    hdf, dpath = store.hdf, store.dpath
+    data = np.array(hdf[f'{dpath}/post_pdfs'][...], dtype=np.float64)
+    blank = np.isnan(data)
+    data[data == 0] = 1e-32                    # keeps the logarithm finite
+    ldata = np.log(data)
+    if evid_weight:
+        evid = np.asarray(hdf[f'{dpath}/evidence'][...])
+        nbest = np.asarray(hdf[f'{dpath}/conv_nbest'][...])
+        d_evid = take_by_components(evid[1:], nbest) - evid[0]
+        d_evid = d_evid - np.nanmin(d_evid)
+        d_evid = d_evid / np.nanmax(d_evid)
+        ldata = ldata * d_evid.reshape((1, 1, 1, 1) + d_evid.shape)
+    cdata = np.zeros_like(data)
+    for i_r in range(data.shape[0]):           # components beyond the run's own number stay empty
+        cdata[i_r, :i_r + 1] = convolve_fill_interp(ldata[i_r, :i_r + 1], kernel)
+    cdata = np.exp(cdata)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        cdata /= np.nansum(cdata, axis=3, keepdims=True)
+    cdata[blank] = np.nan
+    store.create_dataset('conv_post_pdfs', cdata.astype('float32'), group=dpath)
+
+
+def quantize_conv_marginals(store):
+    """'conv_marginals' (r, m, p, M, b, l): quantiles of the convolved PDFs, interpolated on their
+    cumulative sums at the run quantiles 'marg_quantiles' (main.py:1020-1061)."""
+    hdf, dpath = store.hdf, store.dpath
+    bins = np.asarray(hdf[f'{dpath}/pdf_bins'][...])                     # (p, h)
+    quan = np.asarray(hdf[f'{dpath}/marg_quantiles'][...])
+    data = np.asarray(hdf[f'{dpath}/conv_post_pdfs'][...], dtype=np.float64).transpose((0, 1, 2, 4, 5, 3))
+    with np.errstate(invalid='ignore', divide='ignore'):
+        cdf = np.cumsum(data, axis=5) / np.sum(data, axis=5, keepdims=True)
+    margs = nans(cdf.shape[:-1] + (len(quan),))
+    flat, out = cdf.reshape(-1, cdf.shape[-1]), margs.reshape(-1, len(quan))
+    i_p = np.broadcast_to(np.arange(cdf.shape[2]).reshape(1, 1, -1, 1, 1), cdf.shape[:-1]).reshape(-1)
+    for k in np.flatnonzero(np.isfinite(flat[:, -1])):
+        out[k] = np.interp(quan, flat[k], bins[i_p[k]])
+    store.create_dataset('conv_marginals', margs.transpose((0, 1, 2, 5, 3, 4)).astype('float32'), group=dpath)
 
 
 def aggregate_run_products(store):
@@ -250,13 +415,38 @@ def generate_predicted_profiles(store, stack, runner):
                              group=f'{dpath}/model_spec')
 
 
-def postprocess_run(store, stack, runner, par_bins=None, evid_kernel=None):
-    """The reference's `postprocess_run` sequence (main.py:1240-1272) for the steps built
-    here; the PDF convolution / quantisation steps stay with the reference."""
+def create_fits_from_store(store, prefix='source'):
+    """Write the hyperfine-deblended cubes, summed over components, as FITS files
+    `<prefix>_hf_deblended_trans<i>.fits` (main.py:1196-1232).  Needs astropy (import-guarded)."""
+    try:
+        from astropy.io import fits
+    except ImportError as exc:                         # pragma: no cover - optional dependency
+        raise ImportError('create_fits_from_store needs astropy') from exc
+    cube_header = store.read_header(full=True)         # pragma: no cover
+    hdf, dpath = store.hdf, store.dpath                # pragma: no cover
+    model = store.model                                # pragma: no cover
+    vaxis = np.asarray(hdf[f'{dpath}/pdf_bins'][...])[model.IX_VCEN]          # pragma: no cover
+    hfdb = np.asarray(hdf[f'{dpath}/hf_deblended'][...])                      # pragma: no cover  (t, m, S, b, l)
+    for i_t in range(hfdb.shape[0]):                   # pragma: no cover
+        header = cube_header.copy()
+        header.update({'BUNIT': 'K', 'NAXIS3': vaxis.size, 'CRPIX3': 1, 'CDELT3': vaxis[1] - vaxis[0],
+                       'CUNIT3': 'km/s', 'CTYPE3': 'VRAD', 'CRVAL3': vaxis[0], 'SPECSYS': 'LSRK'})
+        fits.PrimaryHDU(np.nansum(hfdb[i_t], axis=0), header).writeto(f'{prefix}_hf_deblended_trans{i_t}.fits',
+                                                                      overwrite=True)
+
+
+def postprocess_run(store, stack, runner, par_bins=None, evid_kernel=None, post_kernel=None, evid_weight=True):
+    """The reference's `postprocess_run` sequence (main.py:1240-1272).  The two convolution stages run when
+    their kernel is given (the reference requires both)."""
     aggregate_run_attributes(store)
     if evid_kernel is not None:
         convolve_evidence(store, evid_kernel)
     aggregate_run_products(store)
     aggregate_run_pdfs(store, par_bins=par_bins)
+    if post_kernel is not None:
+        if evid_kernel is None:
+            raise ValueError('the posterior convolution needs the convolved evidence: pass evid_kernel too')
+        convolve_post_pdfs(store, post_kernel, evid_weight=evid_weight)
+        quantize_conv_marginals(store)
     deblend_hf_intensity(store, stack, runner)
     generate_predicted_profiles(store, stack, runner)

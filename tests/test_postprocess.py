@@ -93,6 +93,89 @@ def test_convolve_evidence_semantics(nb, tmp_path):
     store.close()
 
 
+def test_take_by_components_and_kernels(nb):
+    """Host helpers of the convolution stages (main.py:529-661); the expected numbers were produced by the
+    reference's own functions (tests/golden/make_golden.py imports the reference the same way)."""
+    from nestfit_b200 import postprocess as pp
+    data = np.arange(24, dtype=float).reshape(2, 3, 4)                 # (m, b, l)
+    comps = np.array([[-1, 0, 1, 2], [2, 1, 0, -1], [1, 1, 2, 2]])
+    out = pp.take_by_components(data, comps)
+    assert out.shape == (3, 4) and np.isnan(out[0, 0]) and np.isnan(out[1, 3])
+    assert out[0, 1] == data[0, 0, 1] and out[0, 2] == data[0, 0, 2] and out[0, 3] == data[1, 0, 3]
+    out = pp.take_by_components(data, comps, incl_zero=False)
+    assert np.isnan(out[0, 1]) and np.isnan(out[1, 2]) and out[2, 3] == data[1, 2, 3]
+    wide = np.arange(48, dtype=float).reshape(2, 2, 3, 4)              # (r, m, b, l), components on axis 1
+    assert pp.take_by_components(wide, comps, axis=1).shape == (2, 3, 4)
+    k = pp.get_indep_info_kernel(1.5, nrad=1, sigma_taper=2.0)
+    np.testing.assert_allclose(k, [[0.02048616, 0.01385135, 0.02048616], [0.01385135, 1.0, 0.01385135],
+                                   [0.02048616, 0.01385135, 0.02048616]], rtol=1e-6)
+    assert pp.get_indep_info_kernel(0.3, nrad=0).shape == (1, 1)
+    # a beam much smaller than a pixel: the neighbours carry a full unit of independent information
+    np.testing.assert_allclose(pp.get_indep_info_kernel(0.05, nrad=1), np.ones((3, 3)), atol=1e-12)
+    # circular aperture: exact pixel overlaps add up to the area of the disc
+    mask = pp.apply_circular_mask(np.ones((9, 9)), 3.3)
+    np.testing.assert_allclose(mask.sum(), np.pi * 3.3**2, rtol=1e-12)
+    assert np.allclose(mask, mask.T) and np.allclose(mask, mask[::-1]) and mask[4, 4] == 1.0 and mask[0, 0] == 0.0
+    # default radius = half the kernel width; corner / edge pixels against brute-force supersampling
+    got = pp.apply_circular_mask(np.full((5, 5), 2.0))[0, :3]
+    sub = (np.arange(400) + 0.5) / 400
+    for j, g in enumerate(got):
+        xx, yy = np.meshgrid(-2.5 + sub, -2.5 + j + sub, indexing='ij')
+        assert abs(g - 2.0 * np.mean(xx**2 + yy**2 <= 2.5**2)) < 2e-4
+    assert pp.apply_circular_mask(np.ones((3, 3)), 10.0).sum() == 9.0   # aperture larger than the kernel
+    with pytest.raises(ValueError):
+        pp.apply_circular_mask(np.ones((4, 5)), 1.0)
+
+
+def test_pdf_convolution_and_quantiles(nb, tmp_path):
+    """convolve_post_pdfs / quantize_conv_marginals / extended_masked_evidence (main.py:777-816,956-1061)."""
+    from nestfit_b200 import postprocess as pp
+    # fill-and-interpolate convolution: a NaN inside a constant map is interpolated, the kernel sum is kept,
+    # and the zero fill outside the map shows at the edge
+    img = np.full((1, 7, 9), 2.0)
+    img[0, 3, 4] = np.nan
+    kern = 3.0 * pp.gaussian_kernel2d(0.5)                    # 5 x 5 support
+    out = pp.convolve_fill_interp(img, kern)
+    np.testing.assert_allclose(out[0, 3, 4], 6.0, rtol=1e-12)
+    np.testing.assert_allclose(out[0, 3, 2], 6.0, rtol=1e-12)
+    assert out[0, 0, 0] < 6.0
+    store, _ = fake_store(tmp_path, n_lon=5, n_lat=4, ncomp_max=2)
+    pp.aggregate_run_attributes(store)
+    pp.convolve_evidence(store, 0.7)
+    pp.aggregate_run_products(store)
+    pp.aggregate_run_pdfs(store)
+    d = store.hdf[store.dpath]
+    pdfs = np.asarray(d['post_pdfs'][...])
+    # an identity kernel without evidence weights reproduces the PDFs (zeros floored at 1e-32)
+    ident = np.zeros((3, 3)); ident[1, 1] = 1.0
+    pp.convolve_post_pdfs(store, ident, evid_weight=False)
+    same = np.asarray(d['conv_post_pdfs'][...])
+    assert same.shape == pdfs.shape and np.array_equal(np.isnan(same), np.isnan(pdfs))
+    np.testing.assert_allclose(np.nan_to_num(same), np.nan_to_num(pdfs), atol=1e-6)
+    # a real kernel with evidence weights: still normalised PDFs on the fitted pixels
+    del d['conv_post_pdfs']
+    pp.convolve_post_pdfs(store, pp.gaussian_kernel2d(0.8) * 4.0, evid_weight=True)
+    conv = np.asarray(d['conv_post_pdfs'][...])
+    ok = ~np.isnan(conv[0, 0, 2, 0])
+    assert ok.sum() >= 10
+    np.testing.assert_allclose(np.nansum(conv[0, 0, 2], axis=0)[ok], 1.0, rtol=1e-5)
+    pp.quantize_conv_marginals(store)
+    margs = np.asarray(d['conv_marginals'][...])
+    assert margs.shape == (2, 2, 6, 15, 4, 5)                            # (r, m, p, M, b, l)
+    q = margs[0, 0, 2, :, 1, 1]
+    order = np.argsort(np.asarray(d['marg_quantiles'][...]))
+    assert np.all(np.diff(q[order]) >= 0) and np.isfinite(q).all()
+    bins = np.asarray(d['pdf_bins'][...])[2]
+    assert bins[0] <= q.min() and q.max() <= bins[-1]
+    assert np.isnan(margs[1, 1, :, :, 1, 2]).all()                      # no two-component run at that pixel
+    pp.extended_masked_evidence(store, 0.7, conv=True, lnz_thresh=3)
+    mext = np.asarray(d['mext_evidence'][...])
+    ev = np.asarray(d['conv_evidence'][...])
+    assert mext.shape == (4, 5)
+    assert np.isnan(mext[(ev[1] - ev[0]) > 3]).all()
+    store.close()
+
+
 @pytest.mark.gpu
 def test_predict_loops_match_oracle(nb, tmp_path):
     """peak/integrated intensity, deblended profiles and MAP model cubes against the oracle's
