@@ -15,7 +15,12 @@ from .models.diazenylium import nnhp_predict, DiazenyliumSpectrum, DiazenyliumRu
 from .prior_constructors import get_irdc_priors, get_synth_priors  # noqa: F401
 from .sampler import NestedSamplingBatch, Dumper, run_multinest  # noqa: F401
 from .store import HdfStore, MemGroup  # noqa: F401
-from . import postprocess  # noqa: F401
 from .main import (  # noqa: F401
     NoiseMap, NoiseMapUniform, DataCube, CubeStack, CubeFitter, get_multiproc_indices, get_block_indices,
+)
+from . import postprocess  # noqa: F401
+from .postprocess import (  # noqa: F401
+    take_by_components, apply_circular_mask, get_indep_info_kernel, aggregate_run_attributes, convolve_evidence,
+    extended_masked_evidence, aggregate_run_products, aggregate_run_pdfs, convolve_post_pdfs,
+    quantize_conv_marginals, deblend_hf_intensity, generate_predicted_profiles, postprocess_run,
 )

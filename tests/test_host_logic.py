@@ -160,3 +160,17 @@ def test_fit_cube_argument_checks():
         fitter.fit_cube('unused', nproc=2, blocks_per_gpu=0)
     with pytest.raises(ValueError, match='one CUDA device per process'):
         fitter.fit_cube('unused', nproc=2, devices=[0])
+
+
+def test_public_names_match_reference_package():
+    """Every name the reference exports at package level (nestfit/__init__.py:8-62) exists here."""
+    import nestfit_b200 as nb
+    names = """Distribution Prior ConstantPrior DuplicatePrior OrderedPrior SpacedPrior CenSepPrior
+        ResolvedCenSepPrior ResolvedPlacementPrior PriorTransformer Spectrum Runner Dumper run_multinest
+        NoiseMap NoiseMapUniform DataCube CubeStack HdfStore CubeFitter take_by_components apply_circular_mask
+        get_indep_info_kernel aggregate_run_attributes convolve_evidence extended_masked_evidence
+        aggregate_run_products aggregate_run_pdfs convolve_post_pdfs quantize_conv_marginals deblend_hf_intensity
+        generate_predicted_profiles postprocess_run amm_predict AmmoniaSpectrum AmmoniaRunner nnhp_predict
+        DiazenyliumSpectrum DiazenyliumRunner gauss_predict GaussianRunner""".split()
+    missing = [n for n in names if not hasattr(nb, n)]
+    assert not missing, missing
