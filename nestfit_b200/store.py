@@ -318,6 +318,20 @@ class HdfStore:
         else:
             warnings.warn('Could not insert header: the HDF5 file is closed.', category=RuntimeWarning)
 
+    def read_header(self, full=True):
+        """The stored cube header (`full`) or its two-dimensional map part (main.py:345-352): an
+        ``astropy.io.fits.Header`` when astropy is importable, else a plain dict with the same cards."""
+        assert self.is_open
+        cards = dict(self.hdf['full_header' if full else 'simple_header'].attrs.items())
+        try:
+            from astropy.io import fits
+        except ImportError:
+            return cards
+        header = fits.Header()                  # pragma: no cover - optional dependency
+        for k, v in cards.items():              # pragma: no cover
+            header[k] = v
+        return header                           # pragma: no cover
+
     def create_dataset(self, dset_name, data, group='', clobber=True):
         assert len(dset_name) > 0
         g = self.hdf.require_group(group) if group else self.hdf

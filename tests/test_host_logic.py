@@ -71,6 +71,23 @@ def test_cube_stack_contract(nb):
     assert nb.NoiseMapUniform(0.35).get_noise(0, 0) == 0.35      # reference test_main.py:32-35
 
 
+def test_store_header_round_trip(tmp_path, nb):
+    """insert_header / read_header (main.py:329-352): the map header is the cube header cut to two axes."""
+    rng = np.random.default_rng(0)
+    x = np.linspace(2.369e10, 2.3695e10, 50)
+    hdr = {'SIMPLE': True, 'BITPIX': -32, 'NAXIS': 3, 'NAXIS1': 4, 'NAXIS2': 3, 'NAXIS3': 50, 'CRPIX1': 2.0,
+           'CDELT1': -1e-3, 'CTYPE1': 'GLON-CAR', 'CRVAL1': 30.0, 'CTYPE3': 'FREQ', 'BUNIT': 'K'}
+    cube = nb.DataCube.from_arrays(rng.normal(size=(4, 3, 50)), x, 0.2, trans_id=1, header=hdr)
+    store = nb.HdfStore(str(tmp_path / 'hdr'))
+    store.insert_header(nb.CubeStack([cube]))
+    full, simple = dict(store.read_header(full=True)), dict(store.read_header(full=False))
+    assert full['NAXIS3'] == 50 and full['CTYPE3'] == 'FREQ' and full['BUNIT'] == 'K'
+    assert simple['NAXIS'] == 2 and simple['WCSAXES'] == 2 and simple['CTYPE1'] == 'GLON-CAR'
+    assert 'NAXIS3' not in simple and 'CTYPE3' not in simple
+    assert store.hdf.attrs['naxis1'] == 4 and store.hdf.attrs['naxis2'] == 3
+    store.close()
+
+
 def test_partitions(nb):
     from nestfit_b200.parallel import block_bounds
     idx = nb.get_multiproc_indices((5, 3), 2)          # reference row striping (main.py:565-571)
