@@ -49,3 +49,55 @@ def make_synth_stack(shape, utrans, ncomp_map=None, n_chan=1000, dv=0.07, noise=
     stack.truths = truths
     stack.ncomp_map = ncomp_map.reshape(shape)
     return stack
+
+
+# ---- host-side helpers of the reference's synthetic-data module (nestfit/synth_spectra.py) ----------------
+# parameter sets of `get_test_spectra(kind)` (synth_spectra.py:250-267): two components, parameter-major
+TEST_PARAMS = {
+    0: np.array([-1.0, 1.5, 10.0, 15.0, 4.0, 6.0, 14.5, 15.0, 0.3, 0.6, 0.0, 0.0]),
+    1: np.array([-1.0, 1.0, 12.0, 12.0, 6.0, 6.0, 14.5, 14.6, 0.3, 0.3, 0.0, 0.0]),
+}
+
+
+def test_axes(vchan=0.158):
+    """Frequency axes [Hz, ascending] of the reference's test spectra: v = arange(-30, 30, vchan) km/s in the
+    radio convention about the (1,1) and (2,2) rest frequencies (synth_spectra.py:246-249)."""
+    v = np.arange(-30, 30, vchan)
+    return [np.sort(NU[t] * (1.0 - v / CKMS)) for t in (1, 2)]
+
+
+test_axes.__test__ = False      # not a pytest test
+
+
+class ParamSampler:
+    """Uniform draws of two-component NH3 parameter vectors: the first component at 0 km/s, the second
+    `vsep` away (synth_spectra.py:165-192).  `rng`: numpy Generator (default: a fresh one)."""
+
+    def __init__(self, vsep=(0.16, 3), trot=(3, 30), tex=(2.8, 12), ntot=(13, 16), sigm=(0.15, 2), orth=(0, 0),
+                 rng=None):
+        self.vsep, self.trot, self.tex, self.ntot, self.sigm, self.orth = vsep, trot, tex, ntot, sigm, orth
+        self.rng = np.random.default_rng() if rng is None else rng
+
+    def draw(self):
+        voff = np.array([0.0, self.rng.uniform(*self.vsep)])
+        rest = [self.rng.uniform(*r, size=2) for r in (self.trot, self.tex, self.ntot, self.sigm, self.orth)]
+        return np.concatenate([voff] + rest)
+
+
+def add_noise_to_cube(data, std, rng=None):
+    """`data` plus independent N(0, std^2) noise (synth_spectra.py:160-162)."""
+    rng = np.random.default_rng() if rng is None else rng
+    return data + rng.normal(scale=std, size=data.shape) if std > 0 else data + 0.0
+
+
+def make_fake_header(data, xarr, rest_freq):
+    """Header cards of a synthetic (lon, lat, chan) cube with frequency axis `xarr` [Hz], as a dict
+    (synth_spectra.py:12-37,149-157: the reference pins the reference pixels at the last element)."""
+    return {
+        'WCSAXES': 3, 'CRPIX1': data.shape[0], 'CRPIX2': data.shape[1], 'CRPIX3': xarr.shape[0],
+        'CDELT1': 1e-4, 'CDELT2': 1e-4, 'CDELT3': float(xarr[1] - xarr[0]),
+        'CTYPE1': 'RA---CAR', 'CTYPE2': 'DEC--CAR', 'CTYPE3': 'FREQ', 'CRVAL1': 0, 'CRVAL2': 0,
+        'CRVAL3': float(rest_freq), 'CUNIT1': 'deg', 'CUNIT2': 'deg', 'CUNIT3': 'Hz', 'RESTFRQ': float(rest_freq),
+        'BUNIT': 'K', 'LONPOLE': 0, 'LATPOLE': 180, 'EQUINOX': 2000.0, 'SPECSYS': 'LSRK', 'RADESYS': 'FK5',
+        'SSYSOBS': 'TOPOCENT',
+    }

@@ -191,3 +191,24 @@ def test_public_names_match_reference_package():
         DiazenyliumSpectrum DiazenyliumRunner gauss_predict GaussianRunner""".split()
     missing = [n for n in names if not hasattr(nb, n)]
     assert not missing, missing
+
+
+def test_synthetic_data_helpers(nb):
+    """ParamSampler / add_noise_to_cube / make_fake_header / test axes (nestfit/synth_spectra.py:149-192,243-267)."""
+    from nestfit_b200 import synth
+    ps = synth.ParamSampler(rng=np.random.default_rng(1))
+    draws = np.array([ps.draw() for _ in range(200)])
+    assert draws.shape == (200, 12) and (draws[:, 0] == 0).all()
+    assert (draws[:, 1] >= 0.16).all() and (draws[:, 1] <= 3).all()
+    assert (draws[:, 2:4] >= 3).all() and (draws[:, 2:4] <= 30).all() and (draws[:, 10:] == 0).all()
+    x11, x22 = synth.test_axes()
+    assert x11.shape == (380,) and x11[1] > x11[0] and abs(x11.mean() / synth.NU[1] - 1) < 1e-6
+    assert synth.TEST_PARAMS[0].shape == (12,) and synth.TEST_PARAMS[1][3] == 12.0
+    cube = np.zeros((3, 4, 380))
+    noisy = synth.add_noise_to_cube(cube, 0.2, rng=np.random.default_rng(2))
+    assert abs(noisy.std() - 0.2) < 0.01 and np.array_equal(synth.add_noise_to_cube(cube, 0.0), cube)
+    hdr = synth.make_fake_header(cube, x11, synth.NU[1])
+    assert hdr['CRPIX3'] == 380 and hdr['CTYPE3'] == 'FREQ' and hdr['RESTFRQ'] == synth.NU[1] and hdr['CDELT3'] > 0
+    # the header feeds DataCube.from_arrays and the store's map header
+    dc = nb.DataCube.from_arrays(cube, x11, 0.2, trans_id=1, header=hdr)
+    assert dc.simple_header['CTYPE1'] == 'RA---CAR' and 'CTYPE3' not in dc.simple_header
