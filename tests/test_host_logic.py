@@ -212,3 +212,57 @@ def test_synthetic_data_helpers(nb):
     # the header feeds DataCube.from_arrays and the store's map header
     dc = nb.DataCube.from_arrays(cube, x11, 0.2, trans_id=1, header=hdr)
     assert dc.simple_header['CTYPE1'] == 'RA---CAR' and 'CTYPE3' not in dc.simple_header
+
+
+STUB_FITTER = """
+import time
+from nestfit_b200.main import CubeFitter
+
+
+class StubStack:
+    # just enough of a CubeStack for the store header and the block partition
+    spatial_shape = (6, 5)
+    shape = (6, 5, 8)
+    simple_header = {'NAXIS': 2, 'NAXIS1': 6, 'NAXIS2': 5}
+    full_header = {'NAXIS': 3, 'NAXIS1': 6, 'NAXIS2': 5, 'NAXIS3': 8}
+
+
+class StubFitter(CubeFitter):
+    def fit_block(self, indices, device=0, group_root=None, verbose=False):
+        # stands in for the GPU fit of one block: records which worker (device) took each pixel
+        lon, lat = indices
+        if getattr(self, 'fail_on_device', None) == device:
+            raise RuntimeError('stub failure')
+        for i, j in zip(lon, lat):
+            g = group_root.require_group(f'/pix/{i}/{j}')
+            g.attrs['i_lon'], g.attrs['i_lat'], g.attrs['nbest'] = int(i), int(j), int(device)
+        time.sleep(0.02 * len(lon))
+        return {}
+"""
+
+
+def test_fit_cube_process_fanout_on_cpu(tmp_path, monkeypatch, nb):
+    """fit_cube's process fan-out without a GPU (the block fit is stubbed): two spawned workers, static blocks
+    and queue hand-out; every pixel is written exactly once, into the chunk of the worker that took its block,
+    and the chunks are linked into the table."""
+    import importlib
+    from nestfit_b200.models import ammonia
+    (tmp_path / 'nf_stubfit.py').write_text(STUB_FITTER)
+    monkeypatch.syspath_prepend(str(tmp_path))          # spawned workers inherit sys.path
+    stub = importlib.import_module('nf_stubfit')
+    for k, name in ((1, 'static'), (4, 'queue')):
+        fitter = stub.StubFitter(stub.StubStack(), None, ammonia.AmmoniaRunner, ncomp_max=1)
+        fitter.fit_cube(str(tmp_path / name), nproc=2, blocks_per_gpu=k, devices=[0, 1])
+        store = nb.HdfStore(str(tmp_path / name))
+        assert store.nchunks == 2 and all(p.exists() for p in store.chunk_paths)
+        groups = list(store.iter_pix_groups())
+        assert sorted((g.attrs['i_lon'], g.attrs['i_lat']) for g in groups) == [(i, j) for i in range(6) for j in range(5)]
+        assert {g.attrs['nbest'] for g in groups} == {0, 1}
+        if k == 1:          # one contiguous half of the rows per worker
+            assert {g.attrs['nbest'] for g in groups if g.attrs['i_lon'] < 3} == {0}
+        store.close()
+    # a worker that dies surfaces as an error in the caller (and the others are not left running)
+    fitter = stub.StubFitter(stub.StubStack(), None, ammonia.AmmoniaRunner, ncomp_max=1)
+    fitter.fail_on_device = 1
+    with pytest.raises(RuntimeError, match='GPU worker failed'):
+        fitter.fit_cube(str(tmp_path / 'broken'), nproc=2, blocks_per_gpu=2, devices=[0, 1])
