@@ -266,3 +266,32 @@ def test_fit_cube_process_fanout_on_cpu(tmp_path, monkeypatch, nb):
     fitter.fail_on_device = 1
     with pytest.raises(RuntimeError, match='GPU worker failed'):
         fitter.fit_cube(str(tmp_path / 'broken'), nproc=2, blocks_per_gpu=2, devices=[0, 1])
+
+
+def test_dumper_and_weighted_quantiles(nb):
+    """Dumper (core.pyx:564-609): 15 unweighted quantiles of every parameter column (the last two columns of a
+    posterior array are lnL and the weight), attributes and datasets into an h5py-like group."""
+    from nestfit_b200.sampler import Dumper, MARG_COLS, MARG_QUANTILES, weighted_quantiles
+    rng = np.random.default_rng(3)
+    post = rng.normal(size=(4000, 5))
+    group = nb.MemGroup()
+    d = Dumper(group)
+    assert not d.no_dump and len(d.marginal_cols) == 15 == len(d.quantiles) and MARG_COLS[4] == 'p50'
+    m = d.calc_marginals(post)
+    assert m.shape == (15, 3)
+    np.testing.assert_allclose(m[0], post[:, :3].min(axis=0))
+    np.testing.assert_allclose(m[8], post[:, :3].max(axis=0))
+    np.testing.assert_allclose(m[4], np.median(post[:, :3], axis=0))
+    np.testing.assert_allclose(m[10] - m[9], 2.0, atol=0.12)               # +-1 sigma of a unit normal
+    d.append_attributes(ncomp=2, global_lnZ=-12.5)
+    d.append_datasets(marginals=m, posteriors=post.astype('float32'))
+    d.flush()
+    assert group.attrs['ncomp'] == 2 and np.asarray(group['marginals'][...]).shape == (15, 3)
+    assert np.asarray(group['posteriors'][...]).dtype == np.float32
+    # equal weights: the weighted quantiles agree with the plain ones
+    wq = weighted_quantiles(post[:, :3], np.full(4000, 1 / 4000), MARG_QUANTILES)
+    np.testing.assert_allclose(wq[1:8], m[1:8], atol=0.03)
+    # weights that keep only x > 0 move the median of the first column to the median of the positive half
+    w = (post[:, 0] > 0).astype(float)
+    np.testing.assert_allclose(weighted_quantiles(post[:, :1], w / w.sum(), [0.5])[0, 0],
+                               np.median(post[post[:, 0] > 0, 0]), atol=0.02)
