@@ -49,3 +49,30 @@ def test_shape_errors_mirror_reference(nb):
         nb.Spectrum(np.arange(10.0), np.zeros(10), -1.0)
     with pytest.raises(ValueError, match="not uniform"):
         nb.Spectrum(np.array([0, 1, 2, 4.0]), np.zeros(4), 1.0)
+
+
+def test_missing_library_is_an_error_not_a_fallback(nb, monkeypatch, tmp_path):
+    """The product path has no CPU fallback: without the built CUDA library every entry raises."""
+    from nestfit_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libnestfit_b200.so")
+    with pytest.raises(_lib.NfError, match="no CPU fallback"):
+        _lib.load()
+    x = np.linspace(23.69e9, 23.70e9, 64)
+    with pytest.raises(_lib.NfError):
+        nb.PixelBlock("ammonia", [x, x + 2.8e7], np.zeros((1, 2, 64), np.float32), 0.1, trans_ids=[1, 2])
+
+
+def test_no_device_is_an_error_not_a_fallback(nb):
+    """On a host without a GPU the library loads (symbols, ABI version) but creating a pixel block fails with
+    the device error: nothing is computed on the CPU."""
+    from nestfit_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    n = C.c_int(-1)
+    rc = lib.nf_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    x = np.linspace(23.69e9, 23.70e9, 64)
+    with pytest.raises(_lib.NfError):
+        nb.PixelBlock("ammonia", [x, x + 2.8e7], np.zeros((1, 2, 64), np.float32), 0.1, trans_ids=[1, 2])
