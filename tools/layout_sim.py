@@ -10,6 +10,7 @@ slots, pair trips and (chunk | group, component) records is counted for
   group     group-centric: lines of a component clustered into hyperfine groups (gap > `gap` channels), lanes over
             the group's own window in 32-channel columns from its first channel, two lines x two columns per trip
             (one-column trips for an odd last column), one record per (group, component)
+  group/pair  the same with every pair walking only the columns its own two windows reach
 
 and turned into an instruction estimate with the per-trip / per-record costs measured for v8
 (profiles/r01_source_hotspots.txt).  Usage: python tools/layout_sim.py [n_vectors]
@@ -95,7 +96,7 @@ def count_v8(lo, hi, per_pair_half=False):
     return tot
 
 
-def count_group(lo, hi, gap=24):
+def count_group(lo, hi, gap=24, per_pair_cols=False):
     tot = dict(slots=0, full=0, half=0, records=0, chunks=0, rt_slots=0)
     n_vec, n_spec, ncomp, _ = lo.shape
     for v in range(n_vec):
@@ -124,6 +125,15 @@ def count_group(lo, hi, gap=24):
                     tot['records'] += 1
                     tot['chunks'] += ncol                          # columns accumulated into the model spectrum
                     tot['rt_slots'] += 32 * ncol
+                    if per_pair_cols:          # every pair walks only the columns its own two windows reach
+                        for q in range(npairs):
+                            pl = int(l[a + 2 * q:a + 2 * q + 2].min())
+                            ph = int(h[a + 2 * q:a + 2 * q + 2].max())
+                            nc_ = ((ph - 1 - glo) >> 5) - ((pl - glo) >> 5) + 1
+                            tot['full'] += nc_ // 2; tot['slots'] += 128 * (nc_ // 2)
+                            if nc_ & 1:
+                                tot['half'] += 1; tot['slots'] += 64
+                        continue
                     tot['full'] += npairs * (ncol // 2); tot['slots'] += 128 * npairs * (ncol // 2)
                     if ncol & 1:
                         tot['half'] += npairs; tot['slots'] += 64 * npairs
@@ -152,6 +162,7 @@ def main():
     print(f"{P.shape[0]} vectors; useful Gaussian slots per eval {useful:.0f}")
     rows = [("v8", count_v8(lo, hi)), ("pairhalf", count_v8(lo, hi, per_pair_half=True))]
     rows += [(f"group gap={g}", count_group(lo, hi, gap=g)) for g in (8, 24, 48)]
+    rows += [(f"group/pair {g}", count_group(lo, hi, gap=g, per_pair_cols=True)) for g in (8, 24)]
     print(f"{'layout':14s} {'slots':>8s} {'lane eff':>8s} {'full':>7s} {'half':>7s} {'records':>8s} {'fin/col':>8s} {'instr est':>10s}")
     for name, t in rows:
         m = P.shape[0]
