@@ -21,6 +21,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import ref  # noqa: E402
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from prior_kind_sets import kind_prior_sets  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
 m = ref.load()
@@ -206,9 +208,29 @@ def make_n2hp():
     print("n2hp_golden.npz", (OUT / "n2hp_golden.npz").stat().st_size, "bytes")
 
 
+def make_prior_kinds():
+    """prior_kinds_golden.npz: the compiled reference's transforms through OrderedPrior, SpacedPrior and
+    CenSepPrior for ncomp 1..4 (CenSepPrior leaves the unit-cube values in place for ncomp > 2, core.pyx:313-318)."""
+    rng = np.random.default_rng(20261020)
+    pz = {}
+    for name, t in kind_prior_sets(core).items():
+        for ncomp in (1, 2, 3, 4):
+            U = rng.uniform(size=(64, 6 * ncomp))
+            U[0] = 0.5
+            U[1] = 0.0
+            U[2] = 1.0 - 1e-12
+            pz[f"{name}_u{ncomp}"] = U
+            pz[f"{name}_p{ncomp}"] = ref_transform(t, U, ncomp)
+    np.savez_compressed(OUT / "prior_kinds_golden.npz", **pz)
+    print("prior_kinds_golden.npz", (OUT / "prior_kinds_golden.npz").stat().st_size, "bytes")
+
+
 if __name__ == "__main__":
     if "--only-n2hp" in sys.argv:
         make_n2hp()
+    elif "--only-prior-kinds" in sys.argv:
+        make_prior_kinds()
     else:
         main()
         make_n2hp()
+        make_prior_kinds()

@@ -109,6 +109,26 @@ def test_prior_transform_golden(nb, prior_golden, name, ncomps):
         np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["ordered", "spaced", "censep"])
+def test_prior_kinds_golden(nb, name):
+    """The device prior transform for OrderedPrior, SpacedPrior and CenSepPrior (core.pyx:241-318) against
+    fixtures generated from the compiled reference, ncomp 1..4 (CenSepPrior's unparametrised ncomp > 2 included)."""
+    import sys
+    from pathlib import Path
+    import nestfit_b200.core as nbcore
+    gdir = Path(__file__).resolve().parent / "golden"
+    sys.path.insert(0, str(gdir))
+    from prior_kind_sets import kind_prior_sets
+    g = np.load(gdir / "prior_kinds_golden.npz")
+    ut = kind_prior_sets(nbcore)[name]
+    for ncomp in (1, 2, 3, 4):
+        U, want = g[f"{name}_u{ncomp}"].copy(), g[f"{name}_p{ncomp}"]
+        got = ut.transform_batch(U, ncomp)
+        ok = np.isfinite(want)
+        assert (np.isfinite(got) == ok).all()
+        np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=1e-9)
+
+
 def test_prior_transform_random_vs_oracle(nb):
     ut = nb.get_irdc_priors()
     rng = np.random.default_rng(11)
@@ -287,3 +307,54 @@ def test_predict_loglike_consistency_properties(nb):
     z = own.loglike(P, ncomp, vecs_per_pix=1)
     assert np.all(np.abs(z) <= 1e-9), np.abs(z).max()
     own.close()
+
+
+def _north_star_vectors(nb, rng, n_pix=16, per_pix=384):
+    """configs[1]-shaped pixels (3 components, 2 x 1000 channels, sigma = 0.1 K) with, per pixel, vectors from
+    the posterior bulk outwards: the truth, the truth perturbed on scales 1e-4 ... 0.3 of the prior width,
+    and plain prior draws."""
+    ncomp = 3
+    ut = nb.get_irdc_priors()
+    xs = [orc.bench_axis(1, 1000, 0.07), orc.bench_axis(2, 1000, 0.07)]
+    U0 = rng.uniform(0.15, 0.85, size=(4 * n_pix, 6 * ncomp))
+    T = orc.prior_transform(ut.pack(), U0, ncomp)
+    keep = np.isfinite(T).all(axis=1)
+    U0, T = U0[keep][:n_pix], T[keep][:n_pix]
+    clean = orc.nh3_batch(xs, [1, 2], T, ncomp, want_pred=True)["pred"]
+    data = (clean + rng.normal(0.0, 0.1, clean.shape)).astype(np.float32)
+    scales = 10.0 ** rng.uniform(-4.0, -0.5, size=(n_pix, per_pix, 1))
+    U = np.clip(U0[:, None, :] + scales * rng.normal(size=(n_pix, per_pix, 6 * ncomp)), 1e-6, 1 - 1e-6)
+    U[:, 0] = U0
+    U[:, per_pix // 2:] = rng.uniform(size=(n_pix, per_pix - per_pix // 2, 6 * ncomp))
+    P = orc.prior_transform(ut.pack(), U.reshape(-1, 6 * ncomp), ncomp)
+    bad = ~np.isfinite(P).all(axis=1)
+    P[bad] = np.repeat(T, per_pix, axis=0)[bad]
+    return xs, data, P, per_pix
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lnl_north_star_bound(nb, dtype):
+    """The literal bound of BASELINE.json's north_star on configs[1]-shaped data: |lnL_gpu - lnL_ref| <= 1e-3 for
+    every vector within 1e3 of its pixel's best log-likelihood (the posterior bulk and a thousand e-folds beyond:
+    everything nested sampling weights), and 1e-6 |lnL| for the poor fits outside, where 1e-3
+    absolute is below the resolution the reference's own float-rounded FastExp arguments leave."""
+    rng = np.random.default_rng(20261018)
+    xs, data, P, per_pix = _north_star_vectors(nb, rng)
+    P = P.astype(dtype)
+    n_pix = data.shape[0]
+    blk = nb.PixelBlock("ammonia", xs, data, 0.1, trans_ids=[1, 2])
+    got = blk.loglike(P, 3, vecs_per_pix=per_pix)
+    want = orc.nh3_batch(xs, [1, 2], P.astype(np.float64), 3, data=data.astype(np.float64),
+                         noise=np.full((n_pix, 2), 0.1),
+                         pix_of_vec=(np.arange(P.shape[0]) // per_pix).astype(np.int32))["lnL"]
+    blk.close()
+    err = np.abs(got - want)
+    best = want.reshape(n_pix, per_pix).max(axis=1)
+    near = (np.repeat(best, per_pix) - want) <= 1e3
+    assert near.sum() >= 0.25 * near.size and (~near).sum() >= 0.25 * near.size      # both regimes are populated
+    i_near = int(np.argmax(np.where(near, err, -1.0)))
+    i_far = int(np.argmax(np.where(~near, err / np.abs(want), -1.0)))
+    print(f"\nnorth-star lnL bound ({np.dtype(dtype).name}): bulk max |dlnL| {err[i_near]:.2e} at lnL {want[i_near]:.1f} "
+          f"({near.sum()} vectors); outside max |dlnL|/|lnL| {err[i_far] / abs(want[i_far]):.2e} at lnL {want[i_far]:.4g}")
+    assert err[near].max() <= 1e-3
+    assert (err[~near] <= 1e-6 * np.abs(want[~near])).all()

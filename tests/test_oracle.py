@@ -8,6 +8,8 @@ import pytest
 from oracle import oracle as orc
 from oracle import ref as oref
 
+GOLDEN = __import__('pathlib').Path(__file__).resolve().parent / 'golden'
+
 
 def test_kat_swift_convert():
     # reference test_swift_convert, nestfit/models/ammonia.pyx:517-521
@@ -110,6 +112,26 @@ def test_prior_transform_against_golden(prior_golden, name, ncomps):
         ok = np.isfinite(want)
         assert (np.isfinite(got) == ok).all()
         np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["ordered", "spaced", "censep"])
+def test_prior_kinds_against_golden(name):
+    """OrderedPrior, SpacedPrior, CenSepPrior (core.pyx:241-318) against fixtures of the compiled reference
+    (tests/golden/make_golden.py --only-prior-kinds): the packed plan of nestfit_b200.core through the C oracle."""
+    import sys
+    import nestfit_b200.core as nbcore
+    sys.path.insert(0, str(GOLDEN))
+    from prior_kind_sets import kind_prior_sets
+    g = np.load(GOLDEN / "prior_kinds_golden.npz")
+    packed = kind_prior_sets(nbcore)[name].pack()
+    for ncomp in (1, 2, 3, 4):
+        U, want = g[f"{name}_u{ncomp}"], g[f"{name}_p{ncomp}"]
+        got = orc.prior_transform(packed, U, ncomp)
+        ok = np.isfinite(want)
+        assert (np.isfinite(got) == ok).all()
+        np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=1e-11)
+    if name == "censep":      # ncomp > 2 is not parametrised: the unit-cube values stay in place (core.pyx:313-318)
+        assert np.array_equal(g["censep_p3"][:, :3], g["censep_u3"][:, :3])
 
 
 def test_prior_distribution_kat():
