@@ -172,9 +172,12 @@ typedef struct nf_ns_config {
     int32_t n_prop;      /* proposals per run per lock-step iteration (K)              */
     int32_t max_iter;    /* `maxiter`: cap on nested-sampling iterations per run       */
     int32_t max_samples; /* capacity of the posterior sample (dead + final live pts)   */
-    int32_t bound_update_interval; /* `walks`: random-walk steps per new point (<=1: 20+ndim) */
-    int32_t flags;       /* 0 auto: ellipsoidal rejection, random walk once it stalls;
-                            1 random walk from the start; 2 ellipsoidal rejection only   */
+    int32_t bound_update_interval; /* `walks`: random-walk steps per new point (<=1: 20 + active dims) */
+    int32_t flags;       /* bits 0-1: 0 auto: ellipsoidal rejection, random walk once it stalls;
+                            1 random walk from the start; 2 ellipsoidal rejection only.
+                            bit 2 (4): keep the dimensions the priors overwrite (ConstantPrior rows,
+                            DuplicatePrior's second row) inside the bounding ellipsoid / walk metric
+                            instead of drawing them uniformly on their own                  */
     double tol;          /* `tol`: stop when ln(Z + Lmax X) - ln Z < tol               */
     double efr;          /* `efr`: target sampling efficiency (ellipsoid enlargement)  */
     uint64_t seed;       /* counter-based RNG seed: results are reproducible           */
@@ -203,6 +206,16 @@ int nf_ns_results(const nf_sampler *s, double *lnZ, double *lnZ_err, double *max
  * posterior weight p_i = exp(lnL_i + lnw_i - lnZ).  n = min(n_samples, capacity). */
 int nf_ns_posterior(const nf_sampler *s, int64_t run, int32_t capacity, float *theta,
                     double *lnL, double *lnw);
+/* Posterior products of ALL runs in two calls (what the reference's dumper writes per run,
+ * core.pyx:645-687), replacing one nf_ns_posterior round trip per run:
+ *   nf_ns_products_rows: row_offsets[n_run + 1] (host) -- run r owns rows [off[r], off[r+1]) of the pool:
+ *     its dead points and final live points in death order, logZero points (lnL = -inf) dropped;
+ *   nf_ns_products: `post` (host, may be pageable) receives the float32 pool [rows][ndim + 2] laid out like
+ *     the reference's `posteriors` dataset (theta, lnL, posterior weight; core.pyx:680) with one device-to-host
+ *     copy; `marginals` [n_run][n_q][ndim] = numpy.quantile(theta columns, quantiles) -- unweighted, linear
+ *     interpolation, like Dumper.calc_marginals (core.pyx:596-598) -- sorted on the device.  Either may be NULL. */
+int nf_ns_products_rows(nf_sampler *s, int64_t *row_offsets);
+int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post, double *marginals);
 int nf_ns_stats(const nf_sampler *s, int32_t *lock_iters, int64_t *launches);
 
 /* ---- kernel timing helper (bench / roofline) ---------------------------- */

@@ -307,6 +307,9 @@ int nf_priors_create(int device, const nf_prior_desc *priors, int n_prior, const
     if (!pr) { if (prev >= 0) cudaSetDevice(prev); return NF_ENOMEM; }
     std::memset(pr, 0, sizeof(*pr));
     pr->device = device; pr->n_prior = n_prior; pr->n_dist = n_dist; pr->n_model = n_model; pr->n_tables = n_tables;
+    pr->h_priors = new (std::nothrow) nf_prior_desc[n_prior];
+    if (!pr->h_priors) { delete pr; if (prev >= 0) cudaSetDevice(prev); return NF_ENOMEM; }
+    std::memcpy(pr->h_priors, priors, sizeof(nf_prior_desc) * n_prior);
     cudaError_t e = cudaMalloc(&pr->priors, sizeof(nf_prior_desc) * n_prior);
     if (e == cudaSuccess) e = cudaMemcpy(pr->priors, priors, sizeof(nf_prior_desc) * n_prior, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_dist > 0) {
@@ -331,6 +334,7 @@ int nf_priors_free(nf_priors *pr)
     if (pr->dists) cudaFree(pr->dists);
     if (pr->tables) cudaFree(pr->tables);
     if (prev >= 0) cudaSetDevice(prev);
+    delete[] pr->h_priors;
     delete pr;
     return NF_OK;
 }

@@ -53,8 +53,18 @@ struct nf_sampler {
     double *cand_u, *cand_th, *cand_l; // [n_run][K][ndim], .., [n_run][K]
     int32_t *cand_pix;                 // [n_run][K]
     double *bound;                     // [n_run][ndim + ndim*ndim + 2]: mean, scaled L, {use_cube, -}
-    float *dead_th;                    // [n_run][max_samples][ndim]
-    double *dead_l, *dead_lw;          // [n_run][max_samples]
+    // dead points (then the final live points) of all runs in one pool: run r owns rows
+    // [dead_off[r], dead_off[r] + dead_cap[r]), dead_cap[r] = min(max_samples, (max_samples / nlive_max) nlive[r])
+    float *dead_th;                    // [dead_rows][ndim]
+    double *dead_l, *dead_lw;          // [dead_rows]
+    int64_t *dead_off;                 // [n_run + 1] (device)
+    int32_t *dead_cap;                 // [n_run] (device)
+    int64_t dead_rows;
+    std::vector<int64_t> *h_dead_off;  // host copy
+    // products (nf_ns_products_*): rows kept per run and their offsets in the packed posterior pool
+    int32_t *keep_n;                   // [n_run] (device)
+    int64_t *post_off;                 // [n_run + 1] (device)
+    std::vector<int64_t> *h_post_off;
     double *lnZ, *H, *lmax;            // [n_run]
     int32_t *n_dead, *it, *done, *n_it_lock;
     int64_t *n_eval;
@@ -65,6 +75,8 @@ struct nf_sampler {
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
     int walks;
+    int da;                            // dimensions the likelihood depends on (the others are constant / duplicated)
+    signed char adim[NS_MAX_DIM];      // their indices in the unit-cube vector
     int32_t *n_act_host;               // pinned: {n_act, n_cand}
     cudaStream_t stream;
     int lock_iters;
@@ -149,6 +161,13 @@ __global__ void ns_init_live_kernel(double *live_u, double *live_th, int64_t n_r
     for (int k = 0; k < ndim; ++k) { const double v = rng.uniform(); u[k] = v; th[k] = v; }
 }
 
+// pixel of every initial live point (run r, point p)
+__global__ void ns_live_map_kernel(const int32_t *pix_ids, int32_t *map, int64_t n_run, int nlive_max)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_run * nlive_max) map[idx] = pix_ids[idx / nlive_max];
+}
+
 __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32_t *n_dead, int32_t *it,
                                      int32_t *done, int64_t *n_eval, int32_t *act, const int32_t *nlive,
                                      double *live_l, int64_t n_run, int nlive_max, int32_t *mode,
@@ -170,11 +189,21 @@ __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32
     lmax[r] = m;
 }
 
+// The unit-cube dimensions a run's likelihood depends on.  A ConstantPrior row and the second row of a
+// DuplicatePrior (core.pyx:200-238) are overwritten by the prior transform whatever the cube value is, so the
+// constrained prior is uniform and independent in those dimensions: they are drawn uniformly on their own
+// and kept out of the bounding ellipsoid and of the random-walk metric (an ellipsoid has to span the full
+// [0, 1] of such a dimension, which costs volume -- rejection efficiency -- for nothing).
+struct NsDims {
+    int da;
+    signed char adim[NS_MAX_DIM];
+};
+
 // ---- bounding ellipsoid of the live set (one CTA per active run) -----------
 __global__ void __launch_bounds__(128)
 ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nlive_arr, const int32_t *it_arr,
                  const double *live_u, double *bound, int nlive_max, int ndim, double efr, const int32_t *mode,
-                 const int32_t *coh_step)
+                 const int32_t *coh_step, const NsDims dims)
 {
     __shared__ double s_mean[NS_MAX_DIM];
     __shared__ double s_c[NS_MAX_DIM][NS_MAX_DIM + 1];
@@ -184,11 +213,12 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
     // a random-walk cohort keeps the metric it started with: rebuild only at cohort start
     if (mode[r] == 1 && coh_step[r] != 0) return;
     const int nl = nlive_arr[r];
-    const int tid = threadIdx.x, d = ndim;
-    const double *U = live_u + (int64_t)r * nlive_max * d;
+    const int tid = threadIdx.x, d = dims.da, ds = ndim;      // d: active dimensions; ds: row stride of the live set
+    const double *U = live_u + (int64_t)r * nlive_max * ds;
     if (tid < d) {
         double s = 0.0;
-        for (int p = 0; p < nl; ++p) s += U[p * d + tid];
+        const int ja = dims.adim[tid];
+        for (int p = 0; p < nl; ++p) s += U[p * ds + ja];
         s_mean[tid] = s / (double)nl;
     }
     __syncthreads();
@@ -201,7 +231,8 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
         const int b = e - a * (a + 1) / 2;
         double s = 0.0;
         const double ma = s_mean[a], mb = s_mean[b];
-        for (int p = 0; p < nl; ++p) s += (U[p * d + a] - ma) * (U[p * d + b] - mb);
+        const int ja = dims.adim[a], jb = dims.adim[b];
+        for (int p = 0; p < nl; ++p) s += (U[p * ds + ja] - ma) * (U[p * ds + jb] - mb);
         s /= (double)(nl > 1 ? nl - 1 : 1);
         if (a == b) s += 1e-12;
         s_c[a][b] = s;
@@ -231,7 +262,7 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
         double y[NS_MAX_DIM];
         double r2 = 0.0;
         for (int a = 0; a < d; ++a) {
-            double v = U[p * d + a] - s_mean[a];
+            double v = U[p * ds + dims.adim[a]] - s_mean[a];
             for (int k = 0; k < a; ++k) v -= s_c[a][k] * y[k];
             v /= s_c[a][a];
             y[a] = v;
@@ -256,7 +287,7 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
     const double lnV = fmax(lnV_bound, lnV_target);
     // linear scale applied to L so that the ellipsoid has volume V
     const double scale = exp((lnV - lnVd - lndet) / (double)d);
-    double *B = bound + (int64_t)r * (d + d * d + 2);
+    double *B = bound + (int64_t)r * (ds + ds * ds + 2);      // {mean[d], L[d][d], use_cube, ln V} in the active dimensions
     if (tid < d) B[tid] = s_mean[tid];
     for (int e = tid; e < d * d; e += blockDim.x) {
         const int a = e / d, b = e - a * d;
@@ -280,6 +311,8 @@ struct NsDev {
     double *bound;
     float *dead_th;
     double *dead_l, *dead_lw;
+    const int64_t *dead_off;
+    const int32_t *dead_cap;
     double *lnZ, *H, *lmax;
     int32_t *n_dead, *it, *done;
     int64_t *n_eval;
@@ -287,6 +320,7 @@ struct NsDev {
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
     const int32_t *krun, *cand_off;
+    NsDims dims;
     int K, Kmax, d, nlive_max, max_samples, max_iter, walks, flags;
     double tol, efr;
     uint64_t seed;
@@ -310,29 +344,31 @@ __device__ void unit_ball(Philox &rng, int d, double *y)
 // ---- proposals: K candidates (or K random-walk steps) per active run ---------
 __global__ void ns_propose_kernel(const NsDev D)
 {
-    const int a = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
+    const int kblocks = (D.Kmax + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int a = blockIdx.x / kblocks, k = (blockIdx.x - a * kblocks) * blockDim.x + threadIdx.x;    // (active slot, candidate / chain)
     if (a >= *D.n_act_dev) return;
     const int r = D.act[a];
     if (k >= D.krun[r]) return;
     const int64_t idx = (int64_t)D.cand_off[a] + k;
-    const int d = D.d;
+    const int d = D.d, da = D.dims.da;
     const double *B = D.bound + (int64_t)r * (d + d * d + 2);
     Philox rng(D.seed, (uint32_t)r, (uint32_t)D.lock, (uint32_t)k);
     double u[NS_MAX_DIM], y[NS_MAX_DIM];
     bool ok = false;
+    // the dimensions the likelihood does not see: uniform, whatever the method
+    for (int j = 0; j < d; ++j) u[j] = rng.uniform();
     if (D.mode[r] != 1) {
         // rejection sampling from the bounding ellipsoid (or the unit cube itself)
-        if (B[d + d * d] > 0.5) {
-            for (int j = 0; j < d; ++j) u[j] = rng.uniform();
+        if (B[da + da * da] > 0.5) {
             ok = true;
         } else {
             for (int tries = 0; tries < 64 && !ok; ++tries) {
-                unit_ball(rng, d, y);
+                unit_ball(rng, da, y);
                 ok = true;
-                for (int i = 0; i < d; ++i) {
+                for (int i = 0; i < da; ++i) {
                     double v = B[i];
-                    for (int j = 0; j <= i; ++j) v += B[d + i * d + j] * y[j];
-                    u[i] = v;
+                    for (int j = 0; j <= i; ++j) v += B[da + i * da + j] * y[j];
+                    u[D.dims.adim[i]] = v;
                     if (!(v > 0.0 && v < 1.0)) ok = false;
                 }
             }
@@ -353,13 +389,13 @@ __global__ void ns_propose_kernel(const NsDev D)
             D.chain_moved[(int64_t)r * D.Kmax + k] = 0;
         }
         ok = true;
-        unit_ball(rng, d, y);
+        unit_ball(rng, da, y);
         const double sc = D.scale[r];
-        for (int i = 0; i < d; ++i) {
+        for (int i = 0; i < da; ++i) {
             double v = 0.0;
-            for (int j = 0; j <= i; ++j) v += B[d + i * d + j] * y[j];
-            v = cu[i] + sc * v;
-            u[i] = v;
+            for (int j = 0; j <= i; ++j) v += B[da + i * da + j] * y[j];
+            v = cu[D.dims.adim[i]] + sc * v;
+            u[D.dims.adim[i]] = v;
             if (!(v > 0.0 && v < 1.0)) ok = false;
         }
     }
@@ -378,6 +414,8 @@ struct RunState {
     double mn;          // current worst live log-likelihood and its slot (recomputed after every insertion)
     int im;
     int it, nd;
+    int cap;            // rows this run owns in the dead pool, and its first row
+    int64_t off;
     bool done;
 };
 
@@ -416,13 +454,14 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
         S.H = t1 + t2 - lnZ_new;
     }
     S.lnZ = lnZ_new;
-    if (S.nd < D.max_samples) {
+    if (S.nd < S.cap) {
         const double *th = D.live_th + ((int64_t)r * D.nlive_max + im) * d;
-        float *dt = D.dead_th + ((int64_t)r * D.max_samples + S.nd) * d;
+        const int64_t row = S.off + S.nd;
+        float *dt = D.dead_th + row * d;
         for (int j = lane; j < d; j += 32) dt[j] = (float)th[j];
         if (lane == 0) {
-            D.dead_l[(int64_t)r * D.max_samples + S.nd] = mn;
-            D.dead_lw[(int64_t)r * D.max_samples + S.nd] = lnw;
+            D.dead_l[row] = mn;
+            D.dead_lw[row] = lnw;
         }
         ++S.nd;
     }
@@ -436,7 +475,7 @@ __device__ bool try_insert(const NsDev &D, int r, int nl, int lane, double lnshe
     // MultiNest `tol`: largest possible remaining contribution L_max X_i
     const double lnX = -(double)S.it / (double)nl;
     if (logaddexp(S.lnZ, S.lmax + lnX) - S.lnZ < D.tol) S.done = true;
-    if (S.it >= D.max_iter || S.nd + nl >= D.max_samples) S.done = true;
+    if (S.it >= D.max_iter || S.nd + nl >= S.cap) S.done = true;
     return true;
 }
 
@@ -454,6 +493,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
     RunState S;
     warp_argmin(LL, nl, lane, S.mn, S.im);
     S.lnZ = D.lnZ[r]; S.H = D.H[r]; S.lmax = D.lmax[r]; S.it = D.it[r]; S.nd = D.n_dead[r]; S.done = false;
+    S.cap = D.dead_cap[r]; S.off = D.dead_off[r];
     int64_t nev = D.n_eval[r];
     // ln(1 - exp(-1/nlive)): ln of the prior-mass shell X_{i-1} - X_i relative to X_{i-1}
     const double lnshell = log(-expm1(-1.0 / (double)nl));
@@ -470,7 +510,7 @@ __global__ void __launch_bounds__(128) ns_update_kernel(const NsDev D)
         // windowed acceptance rate; fall back to the random walk when rejection sampling stalls
         int ea = D.eff_acc[r] + n_acc, ep = D.eff_prop[r] + n_ok;
         if (ep >= 512) {
-            if (!(D.flags & 2) && mode == 0 && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
+            if ((D.flags & 3) != 2 && mode == 0 && (double)ea < (double)ep / (1.2 * (double)D.walks)) {
                 mode = 2;                      // hand over to the random walk at the next aligned lock-step
                 if (lane == 0) D.mode[r] = 2;
             }
@@ -608,15 +648,19 @@ ns_compact_kernel(const int32_t *done, int32_t *act, int32_t *n_act_dev, int32_t
 
 // ---- finalisation: add the live points, normalise, pick best-fit / MAP ------
 __global__ void __launch_bounds__(128)
-ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double *live_l, float *dead_th,
-                   double *dead_l, double *dead_lw, double *lnZ_a, double *H_a, int32_t *n_dead_a, const int32_t *it_a,
-                   double *lnZ_err, double *bestfit, double *mapfit, int64_t n_run, int ndim, int nlive_max,
-                   int max_samples)
+ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double *live_l, float *dead_th_pool,
+                   double *dead_l_pool, double *dead_lw_pool, double *lnZ_a, double *H_a, int32_t *n_dead_a,
+                   const int32_t *it_a, double *lnZ_err, double *bestfit, double *mapfit, int64_t n_run, int ndim,
+                   int nlive_max, const int64_t *dead_off, const int32_t *dead_cap)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_run) return;
     const int nl = nlive_arr[r], d = ndim;
+    const int max_samples = dead_cap[r];
+    // this run's rows of the pool
+    float *dead_th = dead_th_pool + dead_off[r] * d;
+    double *dead_l = dead_l_pool + dead_off[r], *dead_lw = dead_lw_pool + dead_off[r];
     int nd = n_dead_a[r];
     double lnZ = lnZ_a[r], H = H_a[r];
     const double lnw_live = -(double)it_a[r] / (double)nl - log((double)nl);   // X_i / nlive
@@ -631,9 +675,9 @@ ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double
         }
         lnZ = lnZ_new;
         const double *th = live_th + (r * nlive_max + p) * d;
-        float *dt = dead_th + (r * max_samples + nd) * d;
+        float *dt = dead_th + (int64_t)nd * d;
         for (int j = lane; j < d; j += 32) dt[j] = (float)th[j];
-        if (lane == 0) { dead_l[r * max_samples + nd] = l; dead_lw[r * max_samples + nd] = lnw_live; }
+        if (lane == 0) { dead_l[nd] = l; dead_lw[nd] = lnw_live; }
         ++nd;
     }
     __syncwarp();
@@ -641,7 +685,7 @@ ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double
     double bl = -INFINITY, bw = -INFINITY;
     int bi = 0, wi = 0;
     for (int p = lane; p < nd; p += 32) {
-        const double l = dead_l[r * max_samples + p], lw = l + dead_lw[r * max_samples + p];
+        const double l = dead_l[p], lw = l + dead_lw[p];
         if (l > bl) { bl = l; bi = p; }
         if (lw > bw) { bw = lw; wi = p; }
     }
@@ -655,14 +699,108 @@ ns_finalize_kernel(const int32_t *nlive_arr, const double *live_th, const double
         if (w2 > bw || (w2 == bw && j2 < wi)) { bw = w2; wi = j2; }
     }
     for (int j = lane; j < d; j += 32) {
-        bestfit[r * d + j] = (double)dead_th[(r * max_samples + bi) * d + j];
-        mapfit[r * d + j] = (double)dead_th[(r * max_samples + wi) * d + j];
+        bestfit[r * d + j] = (double)dead_th[(int64_t)bi * d + j];
+        mapfit[r * d + j] = (double)dead_th[(int64_t)wi * d + j];
     }
     if (lane == 0) {
         lnZ_a[r] = lnZ;
         H_a[r] = H;
         n_dead_a[r] = nd;
         lnZ_err[r] = sqrt(fmax(H, 0.0) / (double)nl);
+    }
+}
+
+
+// ---- posterior products of all runs (what the reference's dumper writes per run) ----------
+// Rows a run keeps: its dead points and final live points without the logZero ones (NaN prior
+// draws among the first live set, lnL = -inf, weight 0).  One warp per run.
+__global__ void __launch_bounds__(128)
+ns_keep_count_kernel(const double *dead_l, const int64_t *dead_off, const int32_t *n_dead, int32_t *keep_n,
+                     int64_t n_run)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_run) return;
+    const double *L = dead_l + dead_off[r];
+    const int nd = n_dead[r];
+    int cnt = 0;
+    for (int p = lane; p < nd; p += 32) cnt += L[p] > -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(NS_FULL, cnt, o);
+    if (lane == 0) keep_n[r] = cnt;
+}
+
+// float32 rows {theta[d], lnL, posterior weight exp(lnL + ln w - ln Z)} in death order: the layout of the
+// reference's `posteriors` dataset (core.pyx:680).  One warp per run, ordered compaction.
+__global__ void __launch_bounds__(128)
+ns_pack_post_kernel(const float *dead_th, const double *dead_l, const double *dead_lw, const int64_t *dead_off,
+                    const int32_t *n_dead, const double *lnZ, const int64_t *post_off, float *post, int64_t n_run,
+                    int d)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_run) return;
+    const int64_t off = dead_off[r];
+    const int nd = n_dead[r], w = d + 2;
+    const double z = lnZ[r];
+    float *out = post + post_off[r] * w;
+    int at = 0;
+    for (int base = 0; base < nd; base += 32) {
+        const int p = base + lane;
+        const double l = p < nd ? dead_l[off + p] : -INFINITY;
+        const bool keep = l > -INFINITY;
+        const unsigned m = __ballot_sync(NS_FULL, keep);
+        if (keep) {
+            float *row = out + (int64_t)(at + __popc(m & ((1u << lane) - 1u))) * w;
+            const float *th = dead_th + (off + p) * d;
+            for (int j = 0; j < d; ++j) row[j] = th[j];
+            row[d] = (float)l;
+            row[d + 1] = (float)exp(l + dead_lw[off + p] - z);
+        }
+        at += __popc(m);
+    }
+}
+
+// numpy.quantile(theta[:, j], q) -- linear interpolation between order statistics, unweighted like the
+// reference's Dumper.calc_marginals (core.pyx:596-598) -- for one (run, parameter) per CTA: the column
+// is sorted by a bitonic network in shared memory (or in `scratch` for runs with more rows than fit).
+__global__ void __launch_bounds__(512)
+ns_marginals_kernel(const float *post, const int64_t *post_off, const int32_t *run_list, int n_list, int d,
+                    const double *quant, int n_q, double *marg, float *scratch, int scratch_stride)
+{
+    extern __shared__ float s_key[];
+    const int item = blockIdx.x;                  // (entry of run_list, parameter)
+    const int e = item / d, j = item - e * d;
+    if (e >= n_list) return;
+    const int r = run_list[e];
+    const int64_t o = post_off[r];
+    const int n = (int)(post_off[r + 1] - o), w = d + 2;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    float *key = scratch ? scratch + (int64_t)item * scratch_stride : s_key;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) key[i] = i < n ? post[(o + i) * w + j] : INFINITY;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int st = k >> 1; st > 0; st >>= 1) {
+            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1)), hi = lo | st;
+                const float a = key[lo], b = key[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if ((int)threadIdx.x < n_q) {
+        double v = nan("");
+        if (n > 0) {
+            const double h = quant[threadIdx.x] * (double)(n - 1);
+            int lo = (int)floor(h);
+            lo = min(max(lo, 0), n - 1);
+            const int hi = min(lo + 1, n - 1);
+            const double a = (double)key[lo], b = (double)key[hi], t = h - (double)lo;
+            v = a + (b - a) * t;                  // numpy's 'linear' method
+        }
+        marg[((int64_t)r * n_q + threadIdx.x) * d + j] = v;
     }
 }
 
@@ -717,7 +855,7 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     cudaGetDevice(&prev);
     if (cudaSetDevice(px->device) != cudaSuccess) return NF_ENODEV;
     nf_sampler *s = new (std::nothrow) nf_sampler();
-    if (!s) return NF_ENOMEM;
+    if (!s) { if (prev >= 0) cudaSetDevice(prev); return NF_ENOMEM; }
     std::memset(s, 0, sizeof(*s));
     s->px = px; s->pr = pr; s->device = px->device; s->ncomp = ncomp; s->flags = model_flags; s->ndim = ndim;
     s->cfg = *cfg; s->n_run = n_run; s->K = cfg->n_prop;
@@ -726,7 +864,23 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     // sum_a k_a <= max(n_act K, target + n_act K) over a shrinking active list
     s->cand_cap = n_run * (int64_t)s->K + (s->Kmax > s->K ? (int64_t)s->cfg.target_batch : 0);
     const size_t R = (size_t)n_run, NL = (size_t)cfg->nlive_max, D = (size_t)ndim, K = (size_t)s->Kmax,
-                 MS = (size_t)cfg->max_samples, CC = (size_t)s->cand_cap;
+                 CC = (size_t)s->cand_cap;
+    // dead-point pool: every run gets rows in proportion to its own live set (not the wave's largest)
+    s->h_dead_off = new (std::nothrow) std::vector<int64_t>((size_t)n_run + 1, 0);
+    s->h_post_off = new (std::nothrow) std::vector<int64_t>((size_t)n_run + 1, 0);
+    std::vector<int32_t> h_cap((size_t)n_run);
+    if (!s->h_dead_off || !s->h_post_off) { delete s->h_dead_off; delete s->h_post_off; delete s; return NF_ENOMEM; }
+    {
+        const int64_t per_live = cfg->max_samples / cfg->nlive_max;       // >= 2 (checked above)
+        for (int64_t r = 0; r < n_run; ++r) {
+            int64_t c = per_live * nlive[r];
+            if (c > cfg->max_samples) c = cfg->max_samples;
+            h_cap[(size_t)r] = (int32_t)c;
+            (*s->h_dead_off)[(size_t)r + 1] = (*s->h_dead_off)[(size_t)r] + c;
+        }
+        s->dead_rows = (*s->h_dead_off)[(size_t)n_run];
+    }
+    const size_t MS = (size_t)s->dead_rows;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     A(dalloc(&s->pix_ids, R)); A(dalloc(&s->nlive, R));
@@ -734,7 +888,8 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->cand_u, CC * D)); A(dalloc(&s->cand_th, CC * D)); A(dalloc(&s->cand_l, CC));
     A(dalloc(&s->cand_pix, CC)); A(dalloc(&s->krun, R)); A(dalloc(&s->cand_off, R));
     A(dalloc(&s->bound, R * (D + D * D + 2)));
-    A(dalloc(&s->dead_th, R * MS * D)); A(dalloc(&s->dead_l, R * MS)); A(dalloc(&s->dead_lw, R * MS));
+    A(dalloc(&s->dead_th, MS * D)); A(dalloc(&s->dead_l, MS)); A(dalloc(&s->dead_lw, MS));
+    A(dalloc(&s->dead_off, R + 1)); A(dalloc(&s->dead_cap, R)); A(dalloc(&s->keep_n, R)); A(dalloc(&s->post_off, R + 1));
     A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
     A(dalloc(&s->n_dead, R)); A(dalloc(&s->it, R)); A(dalloc(&s->done, R)); A(dalloc(&s->n_eval, R));
     A(dalloc(&s->bestfit, R * D)); A(dalloc(&s->mapfit, R * D));
@@ -742,11 +897,40 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->mode, R)); A(dalloc(&s->coh_step, R)); A(dalloc(&s->coh_acc, R)); A(dalloc(&s->eff_acc, R));
     A(dalloc(&s->eff_prop, R)); A(dalloc(&s->chain_moved, R * K)); A(dalloc(&s->lstar, R)); A(dalloc(&s->scale, R));
     A(dalloc(&s->chain_u, R * K * D)); A(dalloc(&s->chain_th, R * K * D)); A(dalloc(&s->chain_l, R * K));
-    s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + ndim;
+    // active dimensions from the prior plan (host copy): rows written by a ConstantPrior and the duplicate
+    // row of a DuplicatePrior do not depend on the cube value
+    {
+        bool dummy[NS_MAX_DIM] = {false};
+        for (int k = 0; k < pr->n_prior && pr->h_priors; ++k) {
+            const nf_prior_desc &p = pr->h_priors[k];
+            const int row = p.kind == NF_PRIOR_CONSTANT ? p.p_ix : (p.kind == NF_PRIOR_DUPLICATE ? p.p_ix2 : -1);
+            if (row >= 0 && row < n_model)
+                for (int c = 0; c < ncomp; ++c) dummy[row * ncomp + c] = true;
+        }
+        // a row another prior writes as well stays active (DuplicatePrior's source row, nested sigma rows)
+        for (int k = 0; k < pr->n_prior && pr->h_priors; ++k) {
+            const nf_prior_desc &p = pr->h_priors[k];
+            if (p.kind != NF_PRIOR_CONSTANT)
+                for (int c = 0; c < ncomp; ++c) dummy[p.p_ix * ncomp + c] = false;
+            if (p.kind == NF_PRIOR_RESOLVED_CENSEP || p.kind == NF_PRIOR_RESOLVED_PLACEMENT) {
+                const nf_prior_desc &q = pr->h_priors[p.nested];
+                if (q.kind != NF_PRIOR_CONSTANT)
+                    for (int c = 0; c < ncomp; ++c) dummy[q.p_ix * ncomp + c] = false;
+            }
+        }
+        s->da = 0;
+        for (int j = 0; j < ndim; ++j)
+            if (!dummy[j] || (cfg->flags & 4)) s->adim[s->da++] = (signed char)j;
+        if (s->da == 0)
+            for (int j = 0; j < ndim; ++j) s->adim[s->da++] = (signed char)j;
+    }
+    s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + s->da;
     A(cudaMallocHost((void **)&s->n_act_host, 2 * sizeof(int32_t)));
     A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(s->nlive, nlive, R * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->dead_off, s->h_dead_off->data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->dead_cap, h_cap.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) { nf_ns_free(s); return (int)e; }
     *out = s;
@@ -763,8 +947,10 @@ int nf_ns_free(nf_sampler *s)
                     s->cand_pix, s->krun, s->cand_off, s->bound, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->lmax, s->lnZ_err,
                     s->n_dead, s->it, s->done, s->n_eval, s->bestfit, s->mapfit, s->act, s->n_act_dev,
                     s->mode, s->coh_step, s->coh_acc, s->eff_acc, s->eff_prop, s->chain_moved, s->lstar, s->scale,
-                    s->chain_u, s->chain_th, s->chain_l};
+                    s->chain_u, s->chain_th, s->chain_l, s->dead_off, s->dead_cap, s->keep_n, s->post_off};
     for (void *p : ptrs) if (p) cudaFree(p);
+    delete s->h_dead_off;
+    delete s->h_post_off;
     if (s->n_act_host) cudaFreeHost(s->n_act_host);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (prev >= 0) cudaSetDevice(prev);
@@ -789,23 +975,18 @@ int nf_ns_run(nf_sampler *s)
         // pixel of every (run, point): reuse cand_pix-like map built on the fly via vecs_per_pix is not
         // possible (runs index arbitrary pixels), so score run by run blocks through an explicit map
         int32_t *map = nullptr;
-        if (cudaMalloc((void **)&map, (size_t)n * sizeof(int32_t)) != cudaSuccess) { rc = NF_ENOMEM; }
+        if (cudaMallocAsync((void **)&map, (size_t)n * sizeof(int32_t), st) != cudaSuccess) { rc = NF_ENOMEM; }
         if (rc == NF_OK) {
-            std::vector<int32_t> h((size_t)n), ids((size_t)R);
-            cudaMemcpy(ids.data(), s->pix_ids, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            for (int64_t r = 0; r < R; ++r)
-                for (int p = 0; p < NL; ++p) h[(size_t)(r * NL + p)] = ids[(size_t)r];
-            cudaMemcpyAsync(map, h.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            ns_live_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->pix_ids, map, R, NL);
             rc = score(s, s->live_th, map, NL, n, s->live_l);
-            cudaStreamSynchronize(st);
-            cudaFree(map);
+            cudaFreeAsync(map, st);
         }
         if (rc == NF_OK) {
             ns_init_state_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(s->lnZ, s->H, s->lmax, s->n_dead, s->it,
                                                                             s->done, s->n_eval, s->act, s->nlive,
                                                                             s->live_l, R, NL, s->mode, s->coh_step,
                                                                             s->coh_acc, s->eff_acc, s->eff_prop,
-                                                                            s->scale, (s->cfg.flags & 1) ? 1 : 0);
+                                                                            s->scale, ((s->cfg.flags & 3) == 1) ? 1 : 0);
             s->launches += 2;
         }
     }
@@ -848,11 +1029,14 @@ int nf_ns_run(nf_sampler *s)
         D.live_u = s->live_u; D.live_th = s->live_th; D.live_l = s->live_l;
         D.cand_u = s->cand_u; D.cand_th = s->cand_th; D.cand_l = s->cand_l; D.cand_pix = s->cand_pix;
         D.bound = s->bound; D.dead_th = s->dead_th; D.dead_l = s->dead_l; D.dead_lw = s->dead_lw;
+        D.dead_off = s->dead_off; D.dead_cap = s->dead_cap;
         D.lnZ = s->lnZ; D.H = s->H; D.lmax = s->lmax; D.n_dead = s->n_dead; D.it = s->it; D.done = s->done;
         D.n_eval = s->n_eval; D.mode = s->mode; D.coh_step = s->coh_step; D.coh_acc = s->coh_acc;
         D.eff_acc = s->eff_acc; D.eff_prop = s->eff_prop; D.chain_moved = s->chain_moved; D.lstar = s->lstar;
         D.scale = s->scale; D.chain_u = s->chain_u; D.chain_th = s->chain_th; D.chain_l = s->chain_l;
         D.krun = s->krun; D.cand_off = s->cand_off;
+        D.dims.da = s->da;
+        std::memcpy(D.dims.adim, s->adim, sizeof(D.dims.adim));
         D.K = K; D.Kmax = s->Kmax; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
         D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
         D.lock = lock;
@@ -860,9 +1044,9 @@ int nf_ns_run(nf_sampler *s)
         if (cand_ub > s->cand_cap) cand_ub = s->cand_cap;
         if (prof) cudaEventRecord(pev[0], st);
         ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->n_act_dev, s->nlive, s->it, s->live_u, s->bound, NL, d,
-                                                s->cfg.efr, s->mode, s->coh_step);
+                                                s->cfg.efr, s->mode, s->coh_step, D.dims);
         if (prof) cudaEventRecord(pev[1], st);
-        ns_propose_kernel<<<dim3((unsigned)((s->Kmax + 127) / 128), (unsigned)n_act), 128, 0, st>>>(D);
+        ns_propose_kernel<<<(unsigned)((s->Kmax + 127) / 128) * (unsigned)n_act, 128, 0, st>>>(D);
         if (prof) cudaEventRecord(pev[2], st);
         // few vectors in flight (tail of a wave): smaller CTA tiles, so that the launch spreads over
         // more SMs and a lock-step's latency drops
@@ -922,7 +1106,7 @@ int nf_ns_run(nf_sampler *s)
     if (rc == NF_OK) {
         ns_finalize_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(
             s->nlive, s->live_th, s->live_l, s->dead_th, s->dead_l, s->dead_lw, s->lnZ, s->H, s->n_dead, s->it,
-            s->lnZ_err, s->bestfit, s->mapfit, R, d, NL, s->cfg.max_samples);
+            s->lnZ_err, s->bestfit, s->mapfit, R, d, NL, s->dead_off, s->dead_cap);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = (int)e;
@@ -967,10 +1151,115 @@ int nf_ns_posterior(const nf_sampler *s, int64_t run, int32_t capacity, float *t
     int32_t n = 0;
     cudaError_t e = cudaMemcpy(&n, s->n_dead + run, 4, cudaMemcpyDeviceToHost);
     if (n > capacity) n = capacity;
-    const size_t MS = (size_t)s->cfg.max_samples, D = (size_t)s->ndim;
-    if (e == cudaSuccess && theta) e = cudaMemcpy(theta, s->dead_th + (size_t)run * MS * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && lnL) e = cudaMemcpy(lnL, s->dead_l + (size_t)run * MS, (size_t)n * 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && lnw) e = cudaMemcpy(lnw, s->dead_lw + (size_t)run * MS, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    const size_t off = (size_t)(*s->h_dead_off)[(size_t)run], D = (size_t)s->ndim;
+    if (e == cudaSuccess && theta) e = cudaMemcpy(theta, s->dead_th + off * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lnL) e = cudaMemcpy(lnL, s->dead_l + off, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lnw) e = cudaMemcpy(lnw, s->dead_lw + off, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (prev >= 0) cudaSetDevice(prev);
+    return (int)e;
+}
+
+
+int nf_ns_products_rows(nf_sampler *s, int64_t *row_offsets)
+{
+    if (!s || !row_offsets) return NF_EINVAL;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(s->device) != cudaSuccess) return NF_ENODEV;
+    const int64_t R = s->n_run;
+    ns_keep_count_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, s->stream>>>(s->dead_l, s->dead_off, s->n_dead,
+                                                                                s->keep_n, R);
+    std::vector<int32_t> keep((size_t)R);
+    cudaError_t e = cudaMemcpyAsync(keep.data(), s->keep_n, (size_t)R * 4, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) {
+        std::vector<int64_t> &off = *s->h_post_off;
+        off[0] = 0;
+        for (int64_t r = 0; r < R; ++r) off[(size_t)r + 1] = off[(size_t)r] + keep[(size_t)r];
+        std::memcpy(row_offsets, off.data(), ((size_t)R + 1) * sizeof(int64_t));
+        e = cudaMemcpy(s->post_off, off.data(), ((size_t)R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
+    }
+    s->launches += 1;
+    if (prev >= 0) cudaSetDevice(prev);
+    return (int)e;
+}
+
+int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post, double *marginals)
+{
+    if (!s || n_q < 0 || n_q > 64 || (n_q > 0 && (!quantiles || !marginals))) return NF_EINVAL;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(s->device) != cudaSuccess) return NF_ENODEV;
+    const int64_t R = s->n_run;
+    const int d = s->ndim, w = d + 2;
+    const std::vector<int64_t> &off = *s->h_post_off;
+    const int64_t rows = off[(size_t)R];
+    cudaStream_t st = s->stream;
+    float *d_post = nullptr, *d_scratch = nullptr;
+    double *d_q = nullptr, *d_marg = nullptr;
+    int32_t *d_list = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    A(cudaMallocAsync((void **)&d_post, (size_t)(rows > 0 ? rows : 1) * w * sizeof(float), st));
+    if (e == cudaSuccess) {
+        ns_pack_post_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(s->dead_th, s->dead_l, s->dead_lw, s->dead_off,
+                                                                            s->n_dead, s->lnZ, s->post_off, d_post, R, d);
+        s->launches += 1;
+    }
+    if (e == cudaSuccess && n_q > 0) {
+        // runs whose column fits in shared memory (<= 32768 rows) and the others (sorted in global scratch)
+        const int SMEM_ROWS = 32768;
+        std::vector<int32_t> small, big;
+        int big_np2 = 0, small_np2 = 1;
+        for (int64_t r = 0; r < R; ++r) {
+            const int64_t n = off[(size_t)r + 1] - off[(size_t)r];
+            int np2 = 1;
+            while (np2 < n) np2 <<= 1;
+            if (n <= SMEM_ROWS) { small.push_back((int32_t)r); small_np2 = np2 > small_np2 ? np2 : small_np2; }
+            else { big.push_back((int32_t)r); big_np2 = np2 > big_np2 ? np2 : big_np2; }
+        }
+        A(cudaMallocAsync((void **)&d_q, (size_t)n_q * sizeof(double), st));
+        A(cudaMallocAsync((void **)&d_marg, (size_t)R * n_q * d * sizeof(double), st));
+        A(cudaMallocAsync((void **)&d_list, (size_t)R * sizeof(int32_t), st));
+        A(cudaMemcpyAsync(d_q, quantiles, (size_t)n_q * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (e == cudaSuccess && !small.empty()) {
+            const size_t smem = (size_t)small_np2 * sizeof(float);
+            A(cudaFuncSetAttribute(ns_marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A(cudaMemcpyAsync(d_list, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            if (e == cudaSuccess)
+                ns_marginals_kernel<<<(unsigned)(small.size() * d), 512, smem, st>>>(d_post, s->post_off, d_list, (int)small.size(), d,
+                                                                                     d_q, n_q, d_marg, nullptr, 0);
+            A(cudaStreamSynchronize(st));          // `small` must outlive the copy
+            s->launches += 1;
+        }
+        // bounded scratch: the long runs go through in batches
+        for (size_t b0 = 0; e == cudaSuccess && b0 < big.size();) {
+            const size_t per = (size_t)big_np2 * d * sizeof(float);
+            size_t nb = (size_t)(1ull << 31) / per;
+            if (nb < 1) nb = 1;
+            if (nb > big.size() - b0) nb = big.size() - b0;
+            A(cudaMallocAsync((void **)&d_scratch, nb * per, st));
+            A(cudaMemcpyAsync(d_list, big.data() + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            if (e == cudaSuccess)
+                ns_marginals_kernel<<<(unsigned)(nb * d), 512, 0, st>>>(d_post, s->post_off, d_list, (int)nb, d, d_q, n_q,
+                                                                       d_marg, d_scratch, big_np2);
+            A(cudaStreamSynchronize(st));
+            if (d_scratch) cudaFreeAsync(d_scratch, st);
+            d_scratch = nullptr;
+            s->launches += 1;
+            b0 += nb;
+        }
+        A(cudaMemcpyAsync(marginals, d_marg, (size_t)R * n_q * d * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (e == cudaSuccess && post && rows > 0)
+        A(cudaMemcpyAsync(post, d_post, (size_t)rows * w * sizeof(float), cudaMemcpyDeviceToHost, st));
+    A(cudaStreamSynchronize(st));
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (d_post) cudaFreeAsync(d_post, st);
+    if (d_q) cudaFreeAsync(d_q, st);
+    if (d_marg) cudaFreeAsync(d_marg, st);
+    if (d_list) cudaFreeAsync(d_list, st);
+    cudaStreamSynchronize(st);
     if (prev >= 0) cudaSetDevice(prev);
     return (int)e;
 }

@@ -20,16 +20,10 @@ _lib.register("nf_ns_free", [_VP])
 _lib.register("nf_ns_results", [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP])
 _lib.register("nf_ns_posterior", [_VP, _I64, C.c_int32, _VP, _VP, _VP])
 _lib.register("nf_ns_stats", [_VP, C.POINTER(C.c_int32), C.POINTER(_I64)])
+_lib.register("nf_ns_products_rows", [_VP, _VP])
+_lib.register("nf_ns_products", [_VP, _VP, _I, _VP, _VP])
 
-# quantiles / labels written per run by the reference (core.pyx:585-594)
-MARG_QUANTILES = np.array([
-    0.00, 0.01, 0.10, 0.25, 0.50, 0.75, 0.90, 0.99, 1.00,
-    1.58655254e-1, 0.84134475,
-    2.27501319e-2, 0.97724987,
-    1.34989803e-3, 0.99865010,
-])
-MARG_COLS = ['min', 'p01', 'p10', 'p25', 'p50', 'p75', 'p90', 'p99', 'max',
-             '1s_lo', '1s_hi', '2s_lo', '2s_hi', '3s_lo', '3s_hi']
+from .store import MARG_COLS, MARG_QUANTILES, run_attr_columns  # noqa: E402  (names re-exported)
 
 
 class NestedSamplingBatch:
@@ -37,10 +31,13 @@ class NestedSamplingBatch:
 
     def __init__(self, block, utrans, ncomp, pix_ids=None, nlive=100, tol=1.0, efr=0.3, n_prop=32, seed=1,
                  max_iter=1_000_000, max_samples=None, cold=False, lte=False, method='auto', walks=0,
-                 n_prop_max=None, target_batch=65536):
+                 n_prop_max=None, target_batch=65536, keep_constant_dims=False):
         """method: 'auto' = ellipsoidal rejection sampling that hands a run over to a
         constrained random walk once its acceptance stalls; 'ellipsoid' / 'rwalk' force one.
-        walks: random-walk steps per new point (0 = 20 + ndim).
+        walks: random-walk steps per new point (0 = 20 + number of dimensions the likelihood depends on).
+        keep_constant_dims: keep the cube dimensions the priors overwrite (ConstantPrior rows, DuplicatePrior's
+        second row) inside the bounding ellipsoid and the walk metric (the round-1 behaviour; default: they are
+        drawn uniformly on their own).
         n_prop_max / target_batch: once few runs are still active each gets up to n_prop_max
         proposals per lock-step (default 16 n_prop) so that a launch keeps ~target_batch vectors."""
         lib = _lib.load()
@@ -58,7 +55,8 @@ class NestedSamplingBatch:
             seed = int(np.random.SeedSequence().generate_state(1)[0])
         self.cfg = NsConfig(nlive_max=nlive_max, n_prop=int(n_prop), max_iter=int(min(max_iter, 2**31 - 1)),
                             max_samples=int(max_samples), bound_update_interval=int(walks),
-                            flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method], tol=float(tol),
+                            flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method] | (4 if keep_constant_dims else 0),
+                            tol=float(tol),
                             efr=float(efr), seed=int(seed),
                             n_prop_max=int(16 * n_prop if n_prop_max is None else n_prop_max),
                             target_batch=int(target_batch))
@@ -95,9 +93,29 @@ class NestedSamplingBatch:
         it, ln = C.c_int32(), C.c_int64()
         lib.nf_ns_stats(self.handle, C.byref(it), C.byref(ln))
         res["lock_iters"], res["launches"] = it.value, ln.value
-        res["truncated"] = res["n_samples"] >= self.cfg.max_samples
+        # a run that filled its share of the dead-point pool stopped before its evidence converged
+        per_live = self.cfg.max_samples // self.cfg.nlive_max
+        res["truncated"] = res["n_samples"] >= np.minimum(self.cfg.max_samples, per_live * self.nlive)
         self._results = res
+        self._batch = None
         return res
+
+    def products_all(self, marginals=True, posteriors=True):
+        """Posterior products of every run with one device pass and one device-to-host copy (instead of one
+        `posterior()` round trip per run): dict(row_offsets [n_run + 1], posteriors float32 [rows, ndim + 2] in
+        the layout of the reference's `posteriors` dataset (core.pyx:680), marginals [n_run, 15, ndim])."""
+        if getattr(self, "_batch", None) is not None:
+            return self._batch
+        self.results
+        lib = _lib.load()
+        off = np.empty(self.n_run + 1, dtype=np.int64)
+        _lib.check(lib.nf_ns_products_rows(self.handle, _lib.ptr(off)), "nf_ns_products_rows")
+        post = np.empty((int(off[-1]), self.ndim + 2), dtype=np.float32) if posteriors else None
+        marg = np.empty((self.n_run, MARG_QUANTILES.size, self.ndim)) if marginals else None
+        _lib.check(lib.nf_ns_products(self.handle, _lib.ptr(MARG_QUANTILES), MARG_QUANTILES.size if marginals else 0,
+                                      _lib.ptr(post), _lib.ptr(marg)), "nf_ns_products")
+        self._batch = dict(row_offsets=off, posteriors=post, marginals=marg)
+        return self._batch
 
     @property
     def results(self):
@@ -126,23 +144,11 @@ class NestedSamplingBatch:
         (core.pyx:645-687), as two dicts."""
         res = self.results
         post = self.posterior(run)
-        k = float(self.ndim)
-        n = float(n_chan_tot)
-        maxL = float(res["max_loglike"][run])
-        nullL = float(null_lnZ)
-        aic = 2 * k - 2 * maxL
-        null_aic = 2 * k - 2 * nullL
-        attrs = {
-            'ncomp': self.ncomp, 'null_lnZ': nullL, 'n_chan_tot': int(n_chan_tot),
-            'n_samples': int(post.shape[0]), 'n_live': int(self.nlive[run]), 'n_params': self.ndim,
-            'global_lnZ': float(res["lnZ"][run]), 'global_lnZ_err': float(res["lnZ_err"][run]),
-            'max_loglike': maxL, 'marg_cols': MARG_COLS, 'marg_quantiles': MARG_QUANTILES,
-            'BIC': np.log(n) * k - 2 * maxL, 'AIC': aic, 'AICc': aic + (2 * k**2 + 2 * k) / (n - k - 1),
-            'null_BIC': np.log(n) * k - 2 * nullL, 'null_AIC': null_aic,
-            'null_AICc': null_aic + (2 * k**2 + 2 * k) / (n - k - 1),
-            # extras (not in the reference): sampler bookkeeping
-            'n_iter': int(res["n_iter"][run]), 'n_evals': int(res["n_evals"][run]),
-        }
+        one = {k: np.asarray(v)[run:run + 1] for k, v in res.items() if isinstance(v, np.ndarray)}
+        cols = run_attr_columns(self.ndim, n_chan_tot, self.nlive[run:run + 1], [null_lnZ], one, [post.shape[0]])
+        attrs = {'ncomp': self.ncomp, 'n_chan_tot': int(n_chan_tot), 'n_params': self.ndim, 'marg_cols': MARG_COLS,
+                 'marg_quantiles': MARG_QUANTILES}
+        attrs.update({k: v[0].item() for k, v in cols.items()})
         dsets = {
             'posteriors': post.astype('float32'),
             # unweighted quantiles over all rows, mirroring core.pyx:596-598

@@ -13,7 +13,9 @@ golden ln Z to compare with, so this port serves two purposes only:
     algorithm run on CPU with the oracle likelihood"), timed by bench.py.
 Only tests/ and bench.py's cpu_baseline leg may import this module.
 
-Scheme (same as the CUDA driver): live set of `nlive` unit-cube points; per step K
+Scheme (same as the CUDA driver): the cube dimensions the priors overwrite (ConstantPrior rows, the second row
+of a DuplicatePrior) are drawn uniformly on their own and stay out of the ellipsoid and the walk metric
+(`active_dims`); live set of `nlive` unit-cube points; per step K
 candidates drawn uniformly from the bounding ellipsoid of the live set (enlarged to the
 larger of 1.2 x the bounding volume and X_i / efr; the unit cube while that volume is
 >= 1/2) are consumed in order against the current worst live point; once the windowed
@@ -62,15 +64,37 @@ def _bound(U, it, nlive, efr):
     return mean, scale * L, use_cube
 
 
+def active_dims(packed_priors, n_model, ncomp):
+    """Indices of the cube dimensions the likelihood depends on (nf_ns_create, nf_sampler.cu): rows written
+    by a ConstantPrior and the duplicate row of a DuplicatePrior are left out unless another prior writes them."""
+    pp, n_p = packed_priors[0], packed_priors[1]
+    dummy = np.zeros(n_model * ncomp, dtype=bool)
+    for k in range(n_p):
+        row = pp[k].p_ix if pp[k].kind == 1 else (pp[k].p_ix2 if pp[k].kind == 2 else -1)
+        if 0 <= row < n_model:
+            dummy[row * ncomp:(row + 1) * ncomp] = True
+    for k in range(n_p):
+        if pp[k].kind != 1:
+            dummy[pp[k].p_ix * ncomp:(pp[k].p_ix + 1) * ncomp] = False
+        if pp[k].kind in (6, 7) and pp[pp[k].nested].kind != 1:
+            q = pp[pp[k].nested]
+            dummy[q.p_ix * ncomp:(q.p_ix + 1) * ncomp] = False
+    act = np.flatnonzero(~dummy)
+    return act if act.size else np.arange(n_model * ncomp)
+
+
 def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None, seed=0, max_iter=1_000_000,
-                    rwalk=False):
+                    rwalk=False, active=None):
     """score(U[B, ndim]) -> lnL[B] (prior transform inside; NaN = not acceptable).
-    `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk').
+    `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk'); `active`: the dimensions
+    inside the ellipsoid / walk metric (default all).
     Returns dict(lnZ, lnZ_err, max_loglike, n_iter, n_evals, n_samples)."""
     rng = np.random.default_rng(seed)
-    d, K = ndim, n_prop
+    K = n_prop
+    act = np.arange(ndim) if active is None else np.asarray(active)
+    d = act.size
     walks = walks or 20 + d
-    U = rng.uniform(size=(nlive, d))
+    U = rng.uniform(size=(nlive, ndim))
     LL = np.asarray(score(U), dtype=np.float64).copy()
     LL[~(LL == LL)] = -np.inf
     st = dict(lnZ=-np.inf, H=0.0, lmax=float(LL.max()), it=0, nd=0, done=False)
@@ -101,13 +125,15 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
 
     mode, ea, ep, sc = (1 if rwalk else 0), 0, 0, 0.3
     while not st['done']:
-        mean, B, use_cube = _bound(U, st['it'], nlive, efr)
+        mean, B, use_cube = _bound(U[:, act], st['it'], nlive, efr)
         if mode == 0:
             if use_cube:
-                cand = rng.uniform(size=(K, d))
+                cand = rng.uniform(size=(K, ndim))
             else:
-                cand = mean + _unit_ball(rng, K, d) @ B.T
-                cand = cand[((cand > 0.0) & (cand < 1.0)).all(axis=1)]
+                ca = mean + _unit_ball(rng, K, d) @ B.T
+                ca = ca[((ca > 0.0) & (ca < 1.0)).all(axis=1)]
+                cand = rng.uniform(size=(ca.shape[0], ndim))
+                cand[:, act] = ca
             if cand.shape[0]:
                 lc = score(cand)
                 n_evals += cand.shape[0]
@@ -129,7 +155,8 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
             lstar = float(LL.min())
             acc = 0
             for _ in range(walks):
-                prop = cu + sc * (_unit_ball(rng, K, d) @ B.T)
+                prop = rng.uniform(size=(K, ndim))
+                prop[:, act] = cu[:, act] + sc * (_unit_ball(rng, K, d) @ B.T)
                 ok = ((prop > 0.0) & (prop < 1.0)).all(axis=1)
                 if ok.any():
                     lp = np.full(K, -np.inf)
@@ -179,7 +206,8 @@ def fit_pixel(xarrs, trans_ids, data, noise, packed_priors, ncomp_max=3, lnZ_thr
             out = orc.nh3_batch(xarrs, trans_ids, np.nan_to_num(th, nan=1.0), ncomp, data=d3, noise=n2)["lnL"]
             out[~np.isfinite(th).all(axis=1)] = np.nan
             return out
-        res = nested_sampling(score, 6 * ncomp, nl, tol=tol, efr=efr, n_prop=n_prop, seed=seed + 7919 * ncomp)
+        res = nested_sampling(score, 6 * ncomp, nl, tol=tol, efr=efr, n_prop=n_prop, seed=seed + 7919 * ncomp,
+                              active=active_dims(packed_priors, 6, ncomp))
         n_evals += res['n_evals']
         lnZ.append(res['lnZ'])
         if res['lnZ'] - old >= lnZ_thresh:

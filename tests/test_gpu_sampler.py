@@ -229,3 +229,43 @@ def test_lnz_agrees_with_cpu_port(nb):
     rc = np.mean([c['n_evals'] / c['n_iter'] for c in cpu])
     rg = np.mean(res["n_evals"] / res["n_iter"])
     assert 0.5 < rc / rg < 2.0, (rc, rg)
+
+
+def test_products_all_matches_per_run(nb):
+    """The batched products pass (device-side packing + column sort, one device-to-host copy; nf_ns_products) gives
+    what the per-run path gives: the float32 `posteriors` rows in death order and numpy.quantile `marginals`
+    (core.pyx:596-598,680), with runs of unequal length and unequal live sets in one pool."""
+    from nestfit_b200.sampler import NestedSamplingBatch, MARG_QUANTILES
+    blk, ut, _ = gauss_problem(nb, seed=8, n_pix=5)
+    ns = NestedSamplingBatch(blk, ut, 1, pix_ids=[0, 1, 2, 3, 4], nlive=[40, 64, 100, 150, 64], tol=0.5, n_prop=16, seed=2)
+    res = ns.run()
+    assert not res["truncated"].any()
+    prod = ns.products_all()
+    off = prod["row_offsets"]
+    assert off[0] == 0 and prod["posteriors"].shape == (off[-1], 5) and prod["posteriors"].dtype == np.float32
+    for r in range(5):
+        post = ns.posterior(r)
+        rows = prod["posteriors"][off[r]:off[r + 1]]
+        assert rows.shape[0] == post.shape[0] == res["n_samples"][r]
+        np.testing.assert_array_equal(rows[:, :3], post[:, :3].astype(np.float32))
+        np.testing.assert_allclose(rows[:, 3], post[:, 3], rtol=1e-6)
+        np.testing.assert_allclose(rows[:, 4], post[:, 4], rtol=2e-5, atol=1e-12)
+        assert abs(rows[:, 4].astype(np.float64).sum() - 1.0) < 1e-4          # posterior weights
+        np.testing.assert_allclose(prod["marginals"][r], np.quantile(post[:, :3], MARG_QUANTILES, axis=0),
+                                   rtol=1e-12, atol=1e-12)
+    ns.close()
+
+
+def test_truncated_runs_are_flagged(nb):
+    """A run that fills its share of the posterior pool stops before its evidence converged and is flagged
+    (CubeFitter repeats such runs with a larger share)."""
+    from nestfit_b200.sampler import NestedSamplingBatch
+    blk, ut, _ = gauss_problem(nb, seed=9, n_pix=2)
+    ns = NestedSamplingBatch(blk, ut, 1, pix_ids=[0, 1], nlive=[50, 50], tol=0.01, n_prop=16, seed=3, max_samples=6 * 50)
+    res = ns.run()
+    assert res["truncated"].all()
+    ns.close()
+    ns = NestedSamplingBatch(blk, ut, 1, pix_ids=[0, 1], nlive=[50, 50], tol=0.01, n_prop=16, seed=3)
+    full = ns.run()
+    assert not full["truncated"].any() and (full["n_iter"] > res["n_iter"]).all()
+    ns.close()
