@@ -143,21 +143,31 @@ class NestedSamplingBatch:
         """Attributes and datasets the reference's dumper writes for one run
         (core.pyx:645-687), as two dicts."""
         res = self.results
-        post = self.posterior(run)
-        one = {k: np.asarray(v)[run:run + 1] for k, v in res.items() if isinstance(v, np.ndarray)}
-        cols = run_attr_columns(self.ndim, n_chan_tot, self.nlive[run:run + 1], [null_lnZ], one, [post.shape[0]])
-        attrs = {'ncomp': self.ncomp, 'n_chan_tot': int(n_chan_tot), 'n_params': self.ndim, 'marg_cols': MARG_COLS,
-                 'marg_quantiles': MARG_QUANTILES}
-        attrs.update({k: v[0].item() for k, v in cols.items()})
-        dsets = {
-            'posteriors': post.astype('float32'),
-            # unweighted quantiles over all rows, mirroring core.pyx:596-598
-            'marginals': np.quantile(post[:, :-2], MARG_QUANTILES, axis=0),
-            'marginals_weighted': weighted_quantiles(post[:, :-2], post[:, -1], MARG_QUANTILES),
-            'bestfit_params': res["bestfit"][run].copy(),
-            'map_params': res["mapfit"][run].copy(),
-        }
-        return attrs, dsets
+        return run_products(self.ncomp, self.ndim, int(self.nlive[run]), null_lnZ, n_chan_tot, self.posterior(run),
+                            res["lnZ"][run], res["lnZ_err"][run], res["max_loglike"][run], res["bestfit"][run],
+                            res["mapfit"][run], n_iter=res["n_iter"][run], n_evals=res["n_evals"][run],
+                            truncated=res["truncated"][run])
+
+
+def run_products(ncomp, ndim, nlive, null_lnZ, n_chan_tot, post, lnZ, lnZ_err, max_loglike, bestfit, mapfit,
+                 n_iter=0, n_evals=0, truncated=False):
+    """What `mn_dump` persists for one run (core.pyx:645-687) from the run's posterior array `post`
+    [n_samples, ndim + 2] (theta, lnL, posterior weight) and its summary numbers: (attrs, datasets)."""
+    res = dict(lnZ=[lnZ], lnZ_err=[lnZ_err], max_loglike=[max_loglike], n_iter=[n_iter], n_evals=[n_evals],
+               truncated=[truncated])
+    cols = run_attr_columns(ndim, n_chan_tot, [nlive], [null_lnZ], res, [post.shape[0]])
+    attrs = {'ncomp': int(ncomp), 'n_chan_tot': int(n_chan_tot), 'n_params': int(ndim), 'marg_cols': MARG_COLS,
+             'marg_quantiles': MARG_QUANTILES}
+    attrs.update({k: v[0].item() for k, v in cols.items()})
+    dsets = {
+        'posteriors': post.astype('float32'),
+        # unweighted quantiles over all rows, mirroring core.pyx:596-598
+        'marginals': np.quantile(post[:, :-2], MARG_QUANTILES, axis=0),
+        'marginals_weighted': weighted_quantiles(post[:, :-2], post[:, -1], MARG_QUANTILES),
+        'bestfit_params': np.array(bestfit, dtype=np.float64),
+        'map_params': np.array(mapfit, dtype=np.float64),
+    }
+    return attrs, dsets
 
 
 def weighted_quantiles(x, w, q):

@@ -84,11 +84,13 @@ def active_dims(packed_priors, n_model, ncomp):
 
 
 def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None, seed=0, max_iter=1_000_000,
-                    rwalk=False, active=None):
+                    rwalk=False, active=None, return_samples=False):
     """score(U[B, ndim]) -> lnL[B] (prior transform inside; NaN = not acceptable).
     `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk'); `active`: the dimensions
     inside the ellipsoid / walk metric (default all).
-    Returns dict(lnZ, lnZ_err, max_loglike, n_iter, n_evals, n_samples)."""
+    Returns dict(lnZ, lnZ_err, max_loglike, n_iter, n_evals, n_samples); with `return_samples` also the dead
+    points and final live points in death order: samples_u [n, ndim], samples_lnL [n], samples_lnw [n]
+    (ln of the prior-mass weight; posterior weight = exp(lnL + lnw - lnZ))."""
     rng = np.random.default_rng(seed)
     K = n_prop
     act = np.arange(ndim) if active is None else np.asarray(active)
@@ -100,6 +102,7 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
     st = dict(lnZ=-np.inf, H=0.0, lmax=float(LL.max()), it=0, nd=0, done=False)
     n_evals = nlive
     lnshell = math.log(-math.expm1(-1.0 / nlive))
+    dead = []
 
     def try_insert(u, lc):
         im = int(np.argmin(LL))
@@ -115,6 +118,8 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
             st['H'] = t1 + t2 - new
         st['lnZ'] = new
         st['nd'] += 1
+        if return_samples:
+            dead.append((U[im].copy(), mn, lnw))
         U[im] = u
         LL[im] = lc
         st['it'] += 1
@@ -184,8 +189,13 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
             t2 = math.exp(lnZ - new) * (H + lnZ) if lnZ > -np.inf else 0.0
             H = t1 + t2 - new
         lnZ = new
-    return dict(lnZ=lnZ, lnZ_err=math.sqrt(max(H, 0.0) / nlive), max_loglike=st['lmax'], n_iter=st['it'],
-                n_evals=n_evals, n_samples=st['nd'] + nlive)
+    out = dict(lnZ=lnZ, lnZ_err=math.sqrt(max(H, 0.0) / nlive), max_loglike=st['lmax'], n_iter=st['it'],
+               n_evals=n_evals, n_samples=st['nd'] + nlive)
+    if return_samples:
+        dead += [(U[p].copy(), float(LL[p]), lnw_live) for p in range(nlive)]
+        out.update(samples_u=np.array([d[0] for d in dead]), samples_lnL=np.array([d[1] for d in dead]),
+                   samples_lnw=np.array([d[2] for d in dead]))
+    return out
 
 
 def fit_pixel(xarrs, trans_ids, data, noise, packed_priors, ncomp_max=3, lnZ_thresh=11.0, nlive=100,
