@@ -295,7 +295,7 @@ def run_ours(args):
 
     gauss_result = run_gauss(nb, lib, _lib, dev, rank, dist) if not args.no_gauss else None
     cube_result = None
-    if args.cube_size > 0:
+    if args.cube_size > 0 or args.scale_cube != "0x0" or args.full_cube:
         del d_params, d_lnl, flush
         torch.cuda.empty_cache()
         cube_result = run_cube_fit(nb, args, rank, world, dev, dist)
@@ -378,7 +378,7 @@ def run_ours(args):
     if gauss_result is not None:
         line["gauss_loglike"] = gauss_result
     if cube is not None:
-        line["cube_fit"] = cube
+        line.update(cube)
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -428,41 +428,140 @@ def run_gauss(nb, lib, _lib, dev, rank, dist):
             "ms_per_launch": ms, "vectors_per_gpu": B, "windowed_gaussians_per_eval": WORK_GAUSS_MODEL, "scaling": "weak"}
 
 
-def run_cube_fit(nb, args, rank, world, dev, dist):
-    """Secondary metric (BASELINE M2): pixels/s of a full evidence-selected cube fit.  Each rank
-    fits its own contiguous block of a (size*world) x size synthetic cube (weak scaling)."""
+def _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag):
+    """The synthetic cube of a cube-fit leg: truth ncomp 0..ncomp_max in spatial blocks,
+    sigma = 0.1 K or a smooth 0.05..0.3 K gradient through `NoiseMap`.  Built once on rank 0 with the predict
+    kernel and shared with the other ranks through /dev/shm (memory-mapped), outside every timed region."""
     import torch
-    from nestfit_b200.synth import make_synth_stack
-    from nestfit_b200.models import ammonia
-    from nestfit_b200.parallel import gather_blocks, max_over_ranks, block_bounds
-    n = args.cube_size
+    from nestfit_b200.synth import make_synth_stack, velocity_axis_hz
     ut = nb.get_irdc_priors()
-    shape = (n * world, n)
+    port = os.environ.get("MASTER_PORT", "0")
+    shm = Path("/dev/shm" if Path("/dev/shm").is_dir() else "/tmp") / f"nf_bench_{port}_{tag}"
     lon, lat = np.indices(shape)
-    ncomp_map = ((lon // max(1, n // 4)) + (lat // max(1, n // 4))) % 4       # 0..3 true components
-    stack = make_synth_stack(shape, ut, ncomp_map=ncomp_map, n_chan=N_CHAN, dv=DV, noise=NOISE, seed=77, device=dev)
-    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=3, lnZ_thresh=11,
-                           mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=32)
-    blocks = nb.get_block_indices(shape, world)
+    b = max(1, min(shape) // 4)
+    ncomp_map = ((lon // b) + (lat // b)) % (ncomp_max + 1)
+    noise = 0.05 + 0.25 * (lon + lat) / float(shape[0] + shape[1] - 2) if noise_grad else NOISE
+    if rank == 0:
+        shm.mkdir(parents=True, exist_ok=True)
+        stack = make_synth_stack(shape, ut, ncomp_map=ncomp_map, n_chan=N_CHAN, dv=DV, noise=noise, seed=seed, device=dev)
+        for t, c in enumerate(stack.cubes):
+            np.save(shm / f"cube{t}.npy", c.data)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    xs = [velocity_axis_hz(1, N_CHAN, DV), velocity_axis_hz(2, N_CHAN, DV)]
+    nm = nb.NoiseMap(np.asarray(noise).T.copy()) if noise_grad else NOISE
+    cubes = [nb.DataCube.from_arrays(np.load(shm / f"cube{t}.npy", mmap_mode="r"), xs[t], nm, trans_id=t + 1,
+                                     header={'CTYPE1': 'RA---SIN', 'CTYPE2': 'DEC--SIN', 'NAXIS1': shape[0],
+                                             'NAXIS2': shape[1]}) for t in (0, 1)]
+    return nb.CubeStack(cubes), ut, ncomp_map, shm
+
+
+def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, tag, blocks_per_gpu):
+    """One cube-fit leg through the public API: `CubeFitter.fit_cube` at N = 1, its SPMD form `fit_cube_rank` (one
+    existing process per GPU, blocks claimed dynamically, one store chunk per rank) at N > 1.  The timed region
+    holds everything the call does: store creation, uploads, the fit, the posterior products, the chunk writes."""
+    import shutil
+    import torch
+    from nestfit_b200.models import ammonia
+    stack, ut, ncomp_map, shm = _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag)
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=ncomp_max, lnZ_thresh=11,
+                           mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=32)
+    store_root = Path(os.environ.get("NF_BENCH_STORE", "/tmp")) / f"nf_bench_store_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+    if rank == 0:
+        shutil.rmtree(store_root, ignore_errors=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    barrier()
     t0 = time.perf_counter()
-    res = fitter.fit_block(blocks[rank], device=dev)
-    torch.cuda.synchronize()
-    secs = max_over_ranks(time.perf_counter() - t0, dist, device=f"cuda:{dev}")
-    nbest = gather_blocks(res['nbest'].astype(np.int64), shape[0] * shape[1], dist, device=f"cuda:{dev}")
-    evals = max_over_ranks(float(res['n_evals']), dist, device=f"cuda:{dev}")
-    if rank != 0:
-        return None
-    agree = float((nbest.reshape(shape) == ncomp_map).mean())
-    out = {"metric": "cube pixels/s fit (ncomp 1-3 evidence model selection)", "value": shape[0] * shape[1] / secs,
-           "unit": "pixels/s", "seconds": secs, "cube": [shape[0], shape[1], 2, N_CHAN], "scaling": "weak",
-           "nlive": "100 + 5*SNR", "tol": 1.0, "likelihood_evals_per_pixel_max_rank": evals / (n * n),
-           "nbest_matches_truth": agree}
-    if world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cube_cpu_baseline(stack, ut, shape, nbest.reshape(shape))
-    return out
+    if world == 1:
+        results = fitter.fit_cube(str(store_root / "cube"), nproc=1, devices=[dev])
+    else:
+        results = fitter.fit_cube_rank(str(store_root / "cube"), rank, world, blocks_per_gpu=blocks_per_gpu, device=dev,
+                                       barrier=barrier)
+    barrier()
+    wall = time.perf_counter() - t0
+    # per-rank bookkeeping -> rank 0
+    mine = {"busy_s": float(sum(r["seconds"] for r in results)), "n_evals": int(sum(r["n_evals"] for r in results)),
+            "n_pix": int(sum(np.asarray(r["nbest"]).size for r in results)), "blocks": len(results),
+            "store_s": float(sum(r.get("store_seconds", 0.0) for r in results)),
+            "store_wait_s": float(sum(r.get("store_wait_seconds", 0.0) for r in results)),
+            "n_truncated": int(sum(r.get("n_truncated", 0) for r in results)), "wall_s": wall,
+            "evals_by_ncomp": np.sum([r["evals_by_ncomp"] for r in results], axis=0).tolist() if results else []}
+    nbest_local = np.full(shape, -9, dtype=np.int64)
+    for r in results:
+        nbest_local[r["i_lon"], r["i_lat"]] = r["nbest"]
+    per_rank = [mine]
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        t = torch.from_numpy(nbest_local).to(f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbest_local = t.cpu().numpy()
+    out = None
+    if rank == 0:
+        wall = max(p["wall_s"] for p in per_rank)
+        n_pix = shape[0] * shape[1]
+        assert sum(p["n_pix"] for p in per_rank) == n_pix and (nbest_local >= 0).all()
+        du = subprocess.run(["du", "-sb", str(store_root)], capture_output=True, text=True).stdout.split()
+        store = nb.HdfStore(str(store_root / "cube"))
+        n_groups = sum(1 for _ in store.iter_pix_groups())
+        store.close()
+        out = {"value": n_pix / wall, "unit": "pixels/s", "seconds": wall, "cube": [shape[0], shape[1], 2, N_CHAN],
+               "ncomp_max": ncomp_max, "noise": "0.05..0.3 K gradient (NoiseMap)" if noise_grad else "0.1 K uniform",
+               "nlive": "100 + 5*SNR", "tol": 1.0, "lnZ_thresh": 11, "blocks_per_gpu": blocks_per_gpu if world > 1 else 1,
+               "api": "CubeFitter.fit_cube(store, nproc=1)" if world == 1 else
+                      f"CubeFitter.fit_cube_rank(store, rank, {world}, blocks_per_gpu={blocks_per_gpu})",
+               "likelihood_evals_per_pixel": sum(p["n_evals"] for p in per_rank) / n_pix,
+               "likelihood_evals_by_ncomp": np.sum([p["evals_by_ncomp"] for p in per_rank], axis=0).tolist(),
+               "nbest_matches_truth": float((np.minimum(nbest_local, ncomp_max) == ncomp_map).mean()),
+               "rank_busy_fraction": [p["busy_s"] / wall for p in per_rank],
+               "rank_blocks": [p["blocks"] for p in per_rank], "rank_pixels": [p["n_pix"] for p in per_rank],
+               "store": {"bytes": int(du[0]) if du else None, "pixel_groups": n_groups, "posteriors": True,
+                         "writer_seconds_sum": sum(p["store_s"] for p in per_rank),
+                         "exposed_wait_seconds_max_rank": max(p["store_wait_s"] for p in per_rank),
+                         "exposed_fraction_of_wall": max(p["store_wait_s"] for p in per_rank) / wall},
+               "runs_repeated_after_truncation": sum(p["n_truncated"] for p in per_rank)}
+        shutil.rmtree(store_root, ignore_errors=True)
+    barrier()
+    if rank == 0:
+        shutil.rmtree(shm, ignore_errors=True)
+    return out, (stack, ut, nbest_local)
+
+
+def run_cube_fit(nb, args, rank, world, dev, dist):
+    """BASELINE metric M2, cube pixels/s with full evidence model selection, through CubeFitter with the store on:
+      * N = 1: configs[2] (size x size, ncomp <= 3, uniform noise) -> `cube_fit_config2`
+      * every N: ONE fixed configs[3]-shaped cube (ncomp <= 4, noise gradient) cut into blocks over the N GPUs
+        -> `cube_fit` (strong scaling)
+      * N = 8 (or --full-cube): the full 512 x 512 configs[3] cube -> `cube_fit_full`."""
+    legs = {}
+    sx, sy = (int(v) for v in args.scale_cube.lower().split("x"))
+    if world == 1 and args.cube_size > 0:
+        out, aux = _cube_leg(nb, (args.cube_size, args.cube_size), 3, False, 77, rank, world, dev, dist, "c2", 1)
+        if rank == 0:
+            out["metric"] = "cube pixels/s fit (configs[2]: ncomp 1-3 evidence model selection, 1 GPU)"
+            out["scaling"] = "n/a (single GPU)"
+            if not args.no_cpu:
+                out["cpu_baseline"] = cube_cpu_baseline(aux[0], aux[1], (args.cube_size, args.cube_size), aux[2])
+            legs["cube_fit_config2"] = out
+    if sx > 0:
+        out, _ = _cube_leg(nb, (sx, sy), 4, True, 78, rank, world, dev, dist, "c3", args.blocks_per_gpu)
+        if rank == 0:
+            out["metric"] = "cube pixels/s fit (configs[3] shape: ncomp <= 4, noise map; one fixed cube over N GPUs)"
+            out["scaling"] = "strong"
+            legs["cube_fit"] = out
+    if args.full_cube or world == 8:
+        out, _ = _cube_leg(nb, (512, 512), 4, True, 79, rank, world, dev, dist, "c3full", args.blocks_per_gpu)
+        if rank == 0:
+            out["metric"] = "cube pixels/s fit (configs[3]: 512x512, ncomp <= 4, noise map)"
+            out["scaling"] = "strong"
+            legs["cube_fit_full"] = out
+    return legs if rank == 0 else None
 
 
 def _cube_cpu_worker(ix):
@@ -474,7 +573,7 @@ def _cube_cpu_worker(ix):
     return r["nbest"], r["n_evals"], time.perf_counter() - t0
 
 
-CUBE_CPU_CAP_S = 180.0      # wall-time cap of the cube-fit CPU baseline: keeps the default run within a few minutes
+CUBE_CPU_CAP_S = 90.0      # wall-time cap of the cube-fit CPU baseline: keeps the default run within a few minutes
 
 
 def _cube_cpu_worker_ix(ix):
@@ -649,8 +748,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-model metric")
-    ap.add_argument("--cube-size", type=int, default=64,
-                    help="side of the per-GPU synthetic cube of the secondary cube-fit metric (0 = skip)")
+    ap.add_argument("--cube-size", type=int, default=128,
+                    help="side of the configs[2] cube fitted at N = 1 (0 = skip)")
+    ap.add_argument("--scale-cube", default="256x128",
+                    help="LONxLAT of the fixed configs[3]-shaped cube fitted at every N (strong scaling; 0x0 = skip)")
+    ap.add_argument("--full-cube", action="store_true", help="also fit the full 512x512 configs[3] cube (default at N = 8)")
+    ap.add_argument("--blocks-per-gpu", type=int, default=8, help="over-decomposition of the multi-GPU cube fit")
     args = ap.parse_args()
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch one process per GPU (the driver does this itself)

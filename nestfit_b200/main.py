@@ -471,13 +471,22 @@ class CubeFitter:
                 if sink is not None:
                     sink.add_pixels(lon[vidx], lat[vidx], nbest)
                 if writer is not None:          # the block's device rows must outlive its samplers
+                    t_w = time.perf_counter()
                     writer.close()
+                    # time the writer worked (mostly hidden behind the next wave) and time the fit waited for it
                     out['store_seconds'] = out.get('store_seconds', 0.0) + writer.seconds
+                    out['store_wait_seconds'] = out.get('store_wait_seconds', 0.0) + time.perf_counter() - t_w
                     writer = _WaveWriter(sink, self.store_posteriors)
                 blk.close()
-        finally:
+        except BaseException:
             if writer is not None:
-                writer.close()
+                try:
+                    writer.close()
+                except BaseException:
+                    pass
+            raise
+        if writer is not None:
+            writer.close()
         out['seconds'] = time.perf_counter() - t0
         out['n_evals'] = n_evals
         return out
@@ -625,7 +634,7 @@ class CubeFitter:
 
 def _block_summary(res, block, worker):
     """What a worker reports back per block: scalars only (the per-pixel arrays are in the store)."""
-    keep = ('seconds', 'n_evals', 'n_retried', 'n_rescued', 'n_truncated', 'store_seconds')
+    keep = ('seconds', 'n_evals', 'n_retried', 'n_rescued', 'n_truncated', 'store_seconds', 'store_wait_seconds')
     out = {k: res[k] for k in keep if k in res}
     out.update(block=block, worker=worker, n_pix=int(np.asarray(res.get('nbest', ())).size))
     for k in ('evals_by_ncomp', 'seconds_by_ncomp'):

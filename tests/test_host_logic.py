@@ -295,3 +295,41 @@ def test_dumper_and_weighted_quantiles(nb):
     w = (post[:, 0] > 0).astype(float)
     np.testing.assert_allclose(weighted_quantiles(post[:, :1], w / w.sum(), [0.5])[0, 0],
                                np.median(post[post[:, 0] > 0, 0]), atol=0.02)
+
+
+def test_fit_cube_rank_spmd_claims(tmp_path, monkeypatch, nb):
+    """fit_cube_rank, the SPMD form of fit_cube for processes that already exist (one per GPU under torchrun):
+    every block is claimed by exactly one rank through exclusive file creation, each rank writes its own chunk,
+    rank 0 creates the store before and links the chunks after the barrier."""
+    import importlib
+    import threading
+    from nestfit_b200.models import ammonia
+    (tmp_path / 'nf_stubfit2.py').write_text(STUB_FITTER)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    stub = importlib.import_module('nf_stubfit2')
+    world = 3
+    bar = threading.Barrier(world)
+    out, errs = {}, []
+
+    def rank_main(r):
+        try:
+            fitter = stub.StubFitter(stub.StubStack(), None, ammonia.AmmoniaRunner, ncomp_max=1)
+            out[r] = fitter.fit_cube_rank(str(tmp_path / 'spmd'), r, world, blocks_per_gpu=4, device=r, barrier=bar.wait)
+        except BaseException as exc:
+            errs.append(exc)
+            bar.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    blocks = sorted(res['block'] for r in out for res in out[r])
+    assert blocks == list(range(12)) and all(len(out[r]) >= 1 for r in out)        # every block exactly once
+    store = nb.HdfStore(str(tmp_path / 'spmd'))
+    assert store.nchunks == world
+    groups = list(store.iter_pix_groups())
+    assert sorted((g.attrs['i_lon'], g.attrs['i_lat']) for g in groups) == [(i, j) for i in range(6) for j in range(5)]
+    assert {g.attrs['nbest'] for g in groups} == {0, 1, 2}                         # written by all three ranks
+    store.close()
