@@ -287,11 +287,24 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     assert np.allclose(hl, lnl_dev, rtol=1e-12, atol=1e-9), "host-call and device-call results differ"
+    # the same call with plain (pageable) numpy buffers, what a reference-side caller hands over
+    pp, pl = P32.copy(), np.empty(B_TOTAL)
 
-    times = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    def e2e_pageable():
+        _lib.check(lib.nf_nh3_loglike_host(blk.handle, _lib.ptr(pp), _lib.NF_F32, None, VPP, B_TOTAL, NCOMP, 0,
+                                           _lib.ptr(pl)), "nf_nh3_loglike_host")
+    e2e_pageable()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_pageable()
+    barrier()
+    e2e_pg_s = time.perf_counter() - t0
+
+    times = torch.tensor([total_ms, e2e_s, e2e_pg_s], dtype=torch.float64, device=f"cuda:{dev}")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(times[0]), float(times[1])
+    total_ms, e2e_s, e2e_pg_s = float(times[0]), float(times[1]), float(times[2])
 
     gauss_result = run_gauss(nb, lib, _lib, dev, rank, dist) if not args.no_gauss else None
     cube_result = None
@@ -332,6 +345,8 @@ def run_ours(args):
     roofline = {
         "bound": bound, "achieved": ach, "peak": peak, "unit": "Gop/s" if bound == "sfu" else "GFLOP/s",
         "frac": ach / peak, "traffic": traffic,
+        "traffic_source": "stored figure: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
+                          "this kernel on this workload (profiles/traffic.json), not measured in this run",
         "peak_source": "measured live by nf_measure_peaks (MUFU.EX2 / FFMA register loops, this box)",
         "work_per_eval": {"n_gauss": n_g, "n_rt": n_rt, "n_setup": N_SETUP_SFU, "sfu_ops": sfu_per_eval,
                           "fp32_flop": flop_per_eval, "counted_on": f"{ns}-vector host sample of this seeded workload (tools/count_work.py: reference window "
@@ -352,7 +367,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(P32.nbytes),
                 "d2h_bytes_per_step": int(B_TOTAL * 8), "steps": n_e2e,
-                "api": "nf_nh3_loglike_host (pinned host buffers, 2-stream pipelined chunks)"},
+                "api": "nf_nh3_loglike_host (pinned host buffers, 2-stream pipelined chunks)",
+                "pageable_host_buffers": {"value": evals * n_e2e / e2e_pg_s, "unit": "evals/s",
+                                          "note": "same call, plain numpy arrays (what a reference-side caller passes)"}},
         "gpu_launches": args.steps,
         "roofline": roofline,
     }
@@ -369,11 +386,18 @@ def run_ours(args):
         lnl_cpu, w = arm.run(P32[:n_s].astype(np.float64), pix_all[:n_s])
         arm.close()
         err = np.abs(lnl_cpu - lnl_dev[:n_s])
+        # BASELINE north_star: 1e-3 absolute within 1e3 of the pixel's best lnL, 1e-6 relative for the poor fits
+        best = np.repeat(lnl_cpu.reshape(-1, VPP).max(axis=1), VPP)
+        near = best - lnl_cpu <= 1e3
+        i_abs, i_rel = int(np.argmax(err)), int(np.argmax(err / np.abs(lnl_cpu)))
         line["cpu_baseline"] = {
             "value": n_s / w, "unit": "evals/s", "cores": arm.cores, "kind": arm.kind,
             "sample": f"first {n_s} vectors of the same batch ({n_s // VPP} pixels), fork pool over all cores",
-            "max_abs_dlnL_vs_gpu": float(err.max()),
-            "parity_ok": bool((err <= 1e-3 + 2e-6 * np.abs(lnl_cpu)).all()),
+            "max_abs_dlnL_vs_gpu": float(err[i_abs]), "lnL_at_max_abs_dlnL": float(lnl_cpu[i_abs]),
+            "max_rel_dlnL_vs_gpu": float(err[i_rel] / abs(lnl_cpu[i_rel])), "lnL_at_max_rel_dlnL": float(lnl_cpu[i_rel]),
+            "vectors_within_1e3_of_best": int(near.sum()),
+            "parity_ok": bool((err[near] <= 1e-3).all() and (err[~near] <= 1e-6 * np.abs(lnl_cpu[~near])).all()),
+            "parity_rule": "|dlnL| <= 1e-3 within 1e3 of the pixel's best lnL, <= 1e-6 |lnL| elsewhere",
         }
     if gauss_result is not None:
         line["gauss_loglike"] = gauss_result

@@ -177,7 +177,9 @@ typedef struct nf_ns_config {
                             1 random walk from the start; 2 ellipsoidal rejection only.
                             bit 2 (4): keep the dimensions the priors overwrite (ConstantPrior rows,
                             DuplicatePrior's second row) inside the bounding ellipsoid / walk metric
-                            instead of drawing them uniformly on their own                  */
+                            instead of drawing them uniformly on their own;
+                            bit 3 (8): ONE bounding ellipsoid instead of the MultiNest-style
+                            decomposition into up to 8 (`mmodal`, core.pyx:727-732)          */
     double tol;          /* `tol`: stop when ln(Z + Lmax X) - ln Z < tol               */
     double efr;          /* `efr`: target sampling efficiency (ellipsoid enlargement)  */
     uint64_t seed;       /* counter-based RNG seed: results are reproducible           */

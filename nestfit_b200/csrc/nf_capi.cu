@@ -103,6 +103,8 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     nf_pixels *px = new (std::nothrow) nf_pixels();
     if (!px) return NF_ENOMEM;
     std::memset(px, 0, sizeof(*px));
+    px->host_mu = new (std::nothrow) std::mutex();
+    if (!px->host_mu) { delete px; return NF_ENOMEM; }
     px->device = device;
     px->model = model;
     px->n_pix = n_pix;
@@ -111,7 +113,7 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     // the hyperfine kernel walks 64-channel chunks, the Gaussian kernel 128-channel chunks
     px->n_pad = model == NF_MODEL_GAUSS ? ((n_chan + 127) / 128) * 128 : ((n_chan + 63) / 64) * 64;
     int rc = fill_meta(px, nu_min, nu_chan, trans_id, rest_freq);
-    if (rc != NF_OK) { delete px; return rc; }
+    if (rc != NF_OK) { delete px->host_mu; delete px; return rc; }
     cudaError_t e;
     const size_t nrow = (size_t)n_pix * n_spec;
     if ((e = cudaMalloc(&px->data, nrow * px->n_pad * sizeof(float))) != cudaSuccess ||
@@ -230,6 +232,8 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
     const size_t off_lnl = off_pix + (((size_t)chunk * 4) + 255) / 256 * 256;
     const size_t off_pred = off_lnl + (((size_t)chunk * 8) + 255) / 256 * 256;
     const size_t total = off_pred + (size_t)chunk * pred_per_vec;
+    // the block's two streams and staging buffers serve one host-buffer call at a time
+    std::lock_guard<std::mutex> host_lock(*px->host_mu);
     int rc = ensure_stage(px, total);
     if (rc != NF_OK) return rc;
 
@@ -414,6 +418,7 @@ int nf_pixels_free(nf_pixels *px)
         if (px->stage_dev[i]) cudaFree(px->stage_dev[i]);
         if (px->streams[i]) cudaStreamDestroy(px->streams[i]);
     }
+    delete px->host_mu;
     delete px;
     return NF_OK;
 }

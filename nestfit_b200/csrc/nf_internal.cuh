@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstdint>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "../../include/nestfit_b200.h"
@@ -51,7 +52,8 @@ struct nf_pixels {
     double *null_lnz;               // [n_pix]
     float *d2chunk;                 // [n_pix][n_spec][n_pad/32]  sum of d^2 over each 32-channel chunk
     NfSpecMeta spec[NF_MAX_SPEC];
-    // pipelined host-call resources
+    // pipelined host-call resources (one host-buffer call at a time per block: guarded by host_mu)
+    std::mutex *host_mu;
     cudaStream_t streams[2];
     void *stage_dev[2];
     void *stage_host[2];

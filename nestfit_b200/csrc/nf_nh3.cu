@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "nf_internal.cuh"
@@ -59,13 +60,25 @@ static const int hd_off[NF_N2HP_NTRANS + 1] = NF_N2HP_LINE_OFFSET_INIT;
 static const double hd_voff[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_VOFF_INIT;
 static const double hd_wt[NF_N2HP_NLINES_TOTAL] = NF_N2HP_LINE_WEIGHT_INIT;
 
+static cudaError_t nh3_upload_device_tables();
+
+// The tables are uploaded once per device, whichever host thread gets there first (samplers of several
+// streams call in concurrently).
 static cudaError_t nh3_init_device_tables()
 {
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e) return e;
-    static bool done[64] = {false};
-    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    if (device < 0 || device >= 64) return nh3_upload_device_tables();
+    static std::once_flag once[64];
+    static cudaError_t result[64];
+    std::call_once(once[device], [device] { result[device] = nh3_upload_device_tables(); });
+    return result[device];
+}
+
+static cudaError_t nh3_upload_device_tables()
+{
+    cudaError_t e = cudaSuccess;
     double freq[NH3_NLINES_ALL];
     float l2w[NH3_NLINES_ALL];
     for (int t = 0; t < NF_NH3_NTRANS; ++t)
@@ -95,7 +108,6 @@ static cudaError_t nh3_init_device_tables()
     if ((e = cudaMemcpyToSymbol(n_iem_xmax, &xmax, sizeof(double)))) return e;
     if ((e = cudaMemcpyToSymbol(n_iem_step, &step, sizeof(double)))) return e;
     if ((e = cudaMemcpyToSymbol(n_iem_inv_dx, &inv_dx, sizeof(double)))) return e;
-    if (device >= 0 && device < 64) done[device] = true;
     return cudaSuccess;
 }
 

@@ -75,6 +75,7 @@ struct nf_sampler {
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
     int walks;
+    int update_every;                  // a run's ellipsoid decomposition is rebuilt every nlive / update_every iterations
     int da;                            // dimensions the likelihood depends on (the others are constant / duplicated)
     signed char adim[NS_MAX_DIM];      // their indices in the unit-cube vector
     int32_t *n_act_host;               // pinned: {n_act, n_cand}
@@ -195,13 +196,24 @@ __global__ void ns_init_state_kernel(double *lnZ, double *H, double *lmax, int32
 // and kept out of the bounding ellipsoid and of the random-walk metric (an ellipsoid has to span the full
 // [0, 1] of such a dimension, which costs volume -- rejection efficiency -- for nothing).
 struct NsDims {
-    int da;
-    signed char adim[NS_MAX_DIM];
+    int da, nfree;
+    signed char adim[NS_MAX_DIM];      // dimensions inside the ellipsoid / walk metric
+    signed char fdim[NS_MAX_DIM];      // the others: uniform on their own
 };
 
-// ---- bounding ellipsoid of the live set (one CTA per active run) -----------
+// ---- bound of the live set: up to NS_MAX_ELL ellipsoids (one CTA per active run) ------------
+// Layout of a run's bound: {n_ell, use_cube, -, -} then NS_MAX_ELL records {mean[d], L[d][d], ln V} in the
+// active dimensions (d = dims.da; the stride is computed with the full ndim).
+#define NS_MAX_ELL 8
+#define NS_KMEANS_ITERS 8
+#define NS_BOUND_HDR 4
+__host__ __device__ inline int64_t ns_ell_stride(int ndim) { return (int64_t)ndim + (int64_t)ndim * ndim + 1; }
+__host__ __device__ inline int64_t ns_bound_stride(int ndim) { return NS_BOUND_HDR + NS_MAX_ELL * ns_ell_stride(ndim); }
+
+// ---- ONE bounding ellipsoid of the live set (one CTA per active run): the light kernel behind mmodal = False,
+// rebuilt every lock-step; same record layout as the decomposition kernel below, n_ell = 1 ----
 __global__ void __launch_bounds__(128)
-ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nlive_arr, const int32_t *it_arr,
+ns_bounds_single_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nlive_arr, const int32_t *it_arr,
                  const double *live_u, double *bound, int nlive_max, int ndim, double efr, const int32_t *mode,
                  const int32_t *coh_step, const NsDims dims)
 {
@@ -287,17 +299,259 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
     const double lnV = fmax(lnV_bound, lnV_target);
     // linear scale applied to L so that the ellipsoid has volume V
     const double scale = exp((lnV - lnVd - lndet) / (double)d);
-    double *B = bound + (int64_t)r * (ds + ds * ds + 2);      // {mean[d], L[d][d], use_cube, ln V} in the active dimensions
-    if (tid < d) B[tid] = s_mean[tid];
+    double *B = bound + (int64_t)r * ns_bound_stride(ds);      // {n_ell, use_cube, -, -} {mean[d], L[d][d], ln V}
+    double *E = B + NS_BOUND_HDR;
+    if (tid < d) E[tid] = s_mean[tid];
     for (int e = tid; e < d * d; e += blockDim.x) {
         const int a = e / d, b = e - a * d;
-        B[d + e] = b <= a ? scale * s_c[a][b] : 0.0;
+        E[d + e] = b <= a ? scale * s_c[a][b] : 0.0;
     }
     if (tid == 0) {
         const bool degenerate = !(f > 0.0) || !isfinite(scale);
-        B[d + d * d] = (lnV > log(0.5) || degenerate) ? 1.0 : 0.0;   // sample the unit cube itself
-        B[d + d * d + 1] = lnV;
+        B[0] = 1.0;
+        B[1] = (lnV > log(0.5) || degenerate) ? 1.0 : 0.0;   // sample the unit cube itself
+        E[d + d * d] = lnV;
     }
+}
+
+
+struct BoundsSmem {
+    double mean[NS_MAX_DIM];
+    double c[NS_MAX_DIM][NS_MAX_DIM + 1];
+    double var[NS_MAX_DIM];            // diagonal of the covariance before the factorisation
+    double red[128];
+    int redi[128];
+    double c0[NS_MAX_DIM], c1[NS_MAX_DIM];
+    int cnt[2];
+    int todo[2 * NS_MAX_ELL];          // cluster labels waiting to be examined
+    int flag;
+};
+
+// Covariance ellipsoid through the farthest of the live points carrying label `want` (any label if lab == nullptr):
+// mean and lower Cholesky factor in S.mean / S.c, the index of the point of largest Mahalanobis radius, the number
+// of points; ln V = max(1.2 x the bounding volume, lnV_min) and the linear scale that gives the factor that volume.
+__device__ void ns_ell_fit(BoundsSmem &S, const double *U, int ds, const NsDims &dims, const short *lab, int want,
+                           int nl, double lnV_base, double &lnV, double &scale, int &far, int &count)
+{
+    const int tid = threadIdx.x, d = dims.da;
+    __syncthreads();
+    if (tid < d) {
+        double sum = 0.0;
+        int n = 0;
+        const int ja = dims.adim[tid];
+        for (int p = 0; p < nl; ++p)
+            if (!lab || lab[p] == want) { sum += U[p * ds + ja]; ++n; }
+        S.mean[tid] = sum / (double)(n > 0 ? n : 1);
+        if (tid == 0) S.cnt[0] = n;
+    }
+    __syncthreads();
+    const int n = S.cnt[0];
+    const int npair = d * (d + 1) / 2;
+    for (int e = tid; e < npair; e += blockDim.x) {
+        int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);      // (a >= b) from the triangular index
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        while (a * (a + 1) / 2 > e) --a;
+        const int b = e - a * (a + 1) / 2;
+        double sum = 0.0;
+        const double ma = S.mean[a], mb = S.mean[b];
+        const int ja = dims.adim[a], jb = dims.adim[b];
+        for (int p = 0; p < nl; ++p)
+            if (!lab || lab[p] == want) sum += (U[p * ds + ja] - ma) * (U[p * ds + jb] - mb);
+        sum /= (double)(n > 1 ? n - 1 : 1);
+        if (a == b) { S.var[a] = sum; sum += 1e-12; }
+        S.c[a][b] = sum;
+        S.c[b][a] = sum;
+    }
+    __syncthreads();
+    if (tid < 32) {          // Cholesky (lower) in place by warp 0: lane <-> row
+        for (int j = 0; j < d; ++j) {
+            double djj = S.c[j][j];
+            for (int k = 0; k < j; ++k) djj -= S.c[j][k] * S.c[j][k];
+            djj = sqrt(fmax(djj, 1e-300));
+            __syncwarp();
+            if (tid == 0) S.c[j][j] = djj;
+            if (tid > j && tid < d) {
+                double v = S.c[tid][j];
+                for (int k = 0; k < j; ++k) v -= S.c[tid][k] * S.c[j][k];
+                S.c[tid][j] = v / djj;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double fmx = -1.0;       // largest Mahalanobis radius over the cluster and where it is
+    int imx = 0;
+    for (int p = tid; p < nl; p += blockDim.x) {
+        if (lab && lab[p] != want) continue;
+        double y[NS_MAX_DIM];
+        double r2 = 0.0;
+        for (int a = 0; a < d; ++a) {
+            double v = U[p * ds + dims.adim[a]] - S.mean[a];
+            for (int k = 0; k < a; ++k) v -= S.c[a][k] * y[k];
+            v /= S.c[a][a];
+            y[a] = v;
+            r2 += v * v;
+        }
+        if (r2 > fmx) { fmx = r2; imx = p; }
+    }
+    S.red[tid] = fmx;
+    S.redi[tid] = imx;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o && (S.red[tid + o] > S.red[tid] || (S.red[tid + o] == S.red[tid] && S.redi[tid + o] < S.redi[tid]))) {
+            S.red[tid] = S.red[tid + o];
+            S.redi[tid] = S.redi[tid + o];
+        }
+        __syncthreads();
+    }
+    const double f = fmax(S.red[0], 1e-300);
+    far = S.redi[0];
+    count = n;
+    double lndet = 0.0;
+    for (int j = 0; j < d; ++j) lndet += log(S.c[j][j]);
+    const double lnVd = 0.5 * d * log(M_PI) - lgamma(0.5 * d + 1.0);
+    lnV = fmax(lnVd + 0.5 * d * log(f) + lndet + log(1.2), lnV_base + log((double)(n > 0 ? n : 1)));
+    scale = exp((lnV - lnVd - lndet) / (double)d);
+    __syncthreads();
+}
+
+// MultiNest-style decomposition (Feroz, Hobson & Bridges 2009, sect. 5.1-5.2, as configured by the reference with
+// mmodal = True, efr = 0.3: core.pyx:727-732): breadth-first 2-means splits of the live set -- seeded at the point of
+// largest Mahalanobis radius and the point farthest from it, distances scaled by the parent's per-dimension spread --
+// kept when the children's volumes add up to less than half the parent's, or when the parent exceeds twice its share
+// X n_c / (efr nlive) of the prior volume and the children are smaller at all.  Every ellipsoid is enlarged to
+// 1.2 x its bounding volume and to at least its share of X / efr.  (oracle/ns_port.py:multi_ellipsoid_bound is the
+// numpy restatement.)  A run in random-walk mode keeps ONE ellipsoid, the metric of its walk, rebuilt at cohort start.
+__global__ void __launch_bounds__(128)
+ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nlive_arr, const int32_t *it_arr,
+                 const double *live_u, double *bound, int nlive_max, int ndim, double efr, const int32_t *mode,
+                 const int32_t *coh_step, const NsDims dims, int lock, int update_every, int multi)
+{
+    __shared__ BoundsSmem S;
+    extern __shared__ short s_lab[];                 // [nlive_max] cluster label of every live point
+    if ((int)blockIdx.x >= *n_act_dev) return;
+    const int r = act[blockIdx.x];
+    const bool walk = mode[r] == 1;
+    if (walk && coh_step[r] != 0) return;            // a cohort keeps the metric it started with
+    double *B = bound + (int64_t)r * ns_bound_stride(ndim);
+    const int nl = nlive_arr[r];
+    const int tid = threadIdx.x, d = dims.da, ds = ndim;
+    const double lnX = -(double)it_arr[r] / (double)nl;
+    const bool use_cube = !walk && lnX - log(efr) > log(0.5);
+    if (use_cube) {
+        if (tid == 0) { B[0] = 0.0; B[1] = 1.0; B[2] = -1.0e30; }
+        return;
+    }
+    // the decomposition is rebuilt every nlive / update_every iterations of the run (MultiNest rebuilds when the
+    // prior volume has shrunk by a set factor); in between the ellipsoids stay valid supersets, the constrained
+    // region only shrinks
+    const int it_now = it_arr[r];
+    if (!walk && B[1] < 0.5 && B[0] >= 1.0 && (double)it_now - B[2] < (double)nl / (double)update_every) return;
+    const double *U = live_u + (int64_t)r * nlive_max * ds;
+    const double lnpv = walk ? -INFINITY : lnX - log(efr) - log((double)nl);
+    const int64_t es = ns_ell_stride(ndim);
+    const int minpts = d + 1;
+    for (int p = tid; p < nl; p += blockDim.x) s_lab[p] = 0;
+    int n_todo = 1, n_done = 0, next_label = 1;
+    if (tid == 0) S.todo[0] = 0;
+    __syncthreads();
+    while (n_todo > 0) {
+        const int label = S.todo[0];
+        __syncthreads();
+        if (tid == 0) for (int k = 1; k < n_todo; ++k) S.todo[k - 1] = S.todo[k];
+        --n_todo;
+        double lnV, scale;
+        int far, cnt;
+        ns_ell_fit(S, U, ds, dims, s_lab, label, nl, lnpv, lnV, scale, far, cnt);
+        bool split = false;
+        int la = 0, lb = 0;
+        if (multi && !walk && cnt >= 2 * minpts && n_todo + n_done + 2 <= NS_MAX_ELL) {
+            // ---- 2-means on the cluster ----
+            if (tid < d) {
+                S.c0[tid] = U[far * ds + dims.adim[tid]];
+                S.mean[tid] = 1.0 / fmax(sqrt(fmax(S.var[tid], 0.0)), 1e-300);      // per-dimension scale (mean is free now)
+            }
+            __syncthreads();
+            double best = -1.0;
+            int ibest = far;
+            for (int p = tid; p < nl; p += blockDim.x) {
+                if (s_lab[p] != label) continue;
+                double d2 = 0.0;
+                for (int a = 0; a < d; ++a) { const double t = (U[p * ds + dims.adim[a]] - S.c0[a]) * S.mean[a]; d2 += t * t; }
+                if (d2 > best) { best = d2; ibest = p; }
+            }
+            S.red[tid] = best; S.redi[tid] = ibest;
+            __syncthreads();
+            for (int o = 64; o > 0; o >>= 1) {
+                if (tid < o && (S.red[tid + o] > S.red[tid] || (S.red[tid + o] == S.red[tid] && S.redi[tid + o] < S.redi[tid]))) {
+                    S.red[tid] = S.red[tid + o]; S.redi[tid] = S.redi[tid + o];
+                }
+                __syncthreads();
+            }
+            if (tid < d) S.c1[tid] = U[S.redi[0] * ds + dims.adim[tid]];
+            la = next_label; lb = next_label + 1;
+            __syncthreads();
+            for (int iter = 0; iter < NS_KMEANS_ITERS; ++iter) {
+                for (int p = tid; p < nl; p += blockDim.x) {
+                    const short cur = s_lab[p];
+                    if (cur != label && cur != la && cur != lb) continue;
+                    double d0 = 0.0, d1 = 0.0;
+                    for (int a = 0; a < d; ++a) {
+                        const double u = U[p * ds + dims.adim[a]], w = S.mean[a];
+                        const double t0 = (u - S.c0[a]) * w, t1 = (u - S.c1[a]) * w;
+                        d0 += t0 * t0; d1 += t1 * t1;
+                    }
+                    s_lab[p] = (short)(d1 < d0 ? lb : la);
+                }
+                __syncthreads();
+                if (tid < d) {
+                    double s0 = 0.0, s1 = 0.0;
+                    int n0 = 0, n1 = 0;
+                    const int ja = dims.adim[tid];
+                    for (int p = 0; p < nl; ++p) {
+                        const short cur = s_lab[p];
+                        if (cur == la) { s0 += U[p * ds + ja]; ++n0; }
+                        else if (cur == lb) { s1 += U[p * ds + ja]; ++n1; }
+                    }
+                    if (tid == 0) { S.cnt[0] = n0; S.cnt[1] = n1; }
+                    if (n0 > 0 && n1 > 0) { S.c0[tid] = s0 / n0; S.c1[tid] = s1 / n1; }
+                }
+                __syncthreads();
+                if (S.cnt[0] == 0 || S.cnt[1] == 0) break;
+            }
+            const int na = S.cnt[0], nb = S.cnt[1];
+            if (na >= minpts && nb >= minpts) {
+                double va, vb, sc2;
+                int f2, c2;
+                ns_ell_fit(S, U, ds, dims, s_lab, la, nl, lnpv, va, sc2, f2, c2);
+                ns_ell_fit(S, U, ds, dims, s_lab, lb, nl, lnpv, vb, sc2, f2, c2);
+                const double m = fmax(va, vb), lnsum = m + log(exp(va - m) + exp(vb - m));
+                split = lnsum < lnV + log(0.5) || (lnV > log(2.0) + log((double)cnt) + lnpv && lnsum < lnV);
+            }
+            if (!split) {          // undo the labels; the parent's factor is recomputed below
+                for (int p = tid; p < nl; p += blockDim.x)
+                    if (s_lab[p] == la || s_lab[p] == lb) s_lab[p] = (short)label;
+                __syncthreads();
+                ns_ell_fit(S, U, ds, dims, s_lab, label, nl, lnpv, lnV, scale, far, cnt);
+            }
+        }
+        if (split) {
+            if (tid == 0) { S.todo[n_todo] = la; S.todo[n_todo + 1] = lb; }
+            n_todo += 2;
+            next_label += 2;
+        } else {
+            double *E = B + NS_BOUND_HDR + (int64_t)n_done * es;
+            if (tid < d) E[tid] = S.mean[tid];
+            for (int e = tid; e < d * d; e += blockDim.x) {
+                const int a = e / d, b = e - a * d;
+                E[d + e] = b <= a ? scale * S.c[a][b] : 0.0;
+            }
+            if (tid == 0) E[d + d * d] = lnV;
+            ++n_done;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { B[0] = (double)n_done; B[1] = 0.0; B[2] = (double)it_now; }
 }
 
 // Device-side view of the sampler state handed to the kernels by value.
@@ -342,6 +596,7 @@ __device__ void unit_ball(Philox &rng, int d, double *y)
 }
 
 // ---- proposals: K candidates (or K random-walk steps) per active run ---------
+template <bool MULTI>
 __global__ void ns_propose_kernel(const NsDev D)
 {
     const int kblocks = (D.Kmax + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -351,26 +606,71 @@ __global__ void ns_propose_kernel(const NsDev D)
     if (k >= D.krun[r]) return;
     const int64_t idx = (int64_t)D.cand_off[a] + k;
     const int d = D.d, da = D.dims.da;
-    const double *B = D.bound + (int64_t)r * (d + d * d + 2);
+    const double *B = D.bound + (int64_t)r * ns_bound_stride(d);
+    const int64_t es = ns_ell_stride(d);
+    const double *E0 = B + NS_BOUND_HDR;                  // first ellipsoid {mean, L, ln V}
     Philox rng(D.seed, (uint32_t)r, (uint32_t)D.lock, (uint32_t)k);
     double u[NS_MAX_DIM], y[NS_MAX_DIM];
     bool ok = false;
     // the dimensions the likelihood does not see: uniform, whatever the method
-    for (int j = 0; j < d; ++j) u[j] = rng.uniform();
+    for (int j = 0; j < D.dims.nfree; ++j) u[D.dims.fdim[j]] = rng.uniform();
     if (D.mode[r] != 1) {
-        // rejection sampling from the bounding ellipsoid (or the unit cube itself)
-        if (B[da + da * da] > 0.5) {
+        // rejection sampling from the union of the bounding ellipsoids (or the unit cube itself)
+        if (B[1] > 0.5) {
+            for (int j = 0; j < da; ++j) u[D.dims.adim[j]] = rng.uniform();
             ok = true;
-        } else {
+        } else if (!MULTI) {
             for (int tries = 0; tries < 64 && !ok; ++tries) {
                 unit_ball(rng, da, y);
                 ok = true;
                 for (int i = 0; i < da; ++i) {
-                    double v = B[i];
-                    for (int j = 0; j <= i; ++j) v += B[da + i * da + j] * y[j];
+                    double v = E0[i];
+                    for (int j = 0; j <= i; ++j) v += E0[da + i * da + j] * y[j];
                     u[D.dims.adim[i]] = v;
                     if (!(v > 0.0 && v < 1.0)) ok = false;
                 }
+            }
+        } else {
+            const int n_ell = (int)B[0];
+            double lnVmax = -INFINITY, wsum = 0.0, wts[NS_MAX_ELL];
+            for (int e = 0; e < n_ell; ++e) lnVmax = fmax(lnVmax, E0[e * es + da + da * da]);
+            for (int e = 0; e < n_ell; ++e) { wts[e] = exp(E0[e * es + da + da * da] - lnVmax); wsum += wts[e]; }
+            for (int tries = 0; tries < 64 && !ok; ++tries) {
+                // pick an ellipsoid by volume, draw a point in it, keep it with probability 1 / (number of
+                // ellipsoids that contain it): uniform over the union
+                int pick = 0;
+                if (n_ell > 1) {
+                    double t = rng.uniform() * wsum;
+                    while (pick < n_ell - 1 && t >= wts[pick]) { t -= wts[pick]; ++pick; }
+                }
+                const double *E = E0 + pick * es;
+                unit_ball(rng, da, y);
+                ok = true;
+                double x[NS_MAX_DIM];
+                for (int i = 0; i < da; ++i) {
+                    double v = E[i];
+                    for (int j = 0; j <= i; ++j) v += E[da + i * da + j] * y[j];
+                    x[i] = v;
+                    if (!(v > 0.0 && v < 1.0)) ok = false;
+                }
+                if (ok && n_ell > 1) {
+                    int q = 1;
+                    for (int e = 0; e < n_ell; ++e) {
+                        if (e == pick) continue;
+                        const double *F = E0 + e * es;
+                        double r2 = 0.0;
+                        for (int i = 0; i < da && r2 <= 1.0; ++i) {        // forward substitution L z = x - mean
+                            double v = x[i] - F[i];
+                            for (int j = 0; j < i; ++j) v -= F[da + i * da + j] * y[j];
+                            v /= F[da + i * da + i];
+                            y[i] = v;
+                            r2 += v * v;
+                        }
+                        q += r2 <= 1.0;
+                    }
+                    if (q > 1 && rng.uniform() * (double)q >= 1.0) ok = false;
+                }
+                if (ok) for (int i = 0; i < da; ++i) u[D.dims.adim[i]] = x[i];
             }
         }
     } else {
@@ -393,7 +693,7 @@ __global__ void ns_propose_kernel(const NsDev D)
         const double sc = D.scale[r];
         for (int i = 0; i < da; ++i) {
             double v = 0.0;
-            for (int j = 0; j <= i; ++j) v += B[da + i * da + j] * y[j];
+            for (int j = 0; j <= i; ++j) v += E0[da + i * da + j] * y[j];
             v = cu[D.dims.adim[i]] + sc * v;
             u[D.dims.adim[i]] = v;
             if (!(v > 0.0 && v < 1.0)) ok = false;
@@ -887,7 +1187,8 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->live_u, R * NL * D)); A(dalloc(&s->live_th, R * NL * D)); A(dalloc(&s->live_l, R * NL));
     A(dalloc(&s->cand_u, CC * D)); A(dalloc(&s->cand_th, CC * D)); A(dalloc(&s->cand_l, CC));
     A(dalloc(&s->cand_pix, CC)); A(dalloc(&s->krun, R)); A(dalloc(&s->cand_off, R));
-    A(dalloc(&s->bound, R * (D + D * D + 2)));
+    A(dalloc(&s->bound, R * (size_t)ns_bound_stride(ndim)));
+    if (e == cudaSuccess) e = cudaMemset(s->bound, 0, R * (size_t)ns_bound_stride(ndim) * sizeof(double));
     A(dalloc(&s->dead_th, MS * D)); A(dalloc(&s->dead_l, MS)); A(dalloc(&s->dead_lw, MS));
     A(dalloc(&s->dead_off, R + 1)); A(dalloc(&s->dead_cap, R)); A(dalloc(&s->keep_n, R)); A(dalloc(&s->post_off, R + 1));
     A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
@@ -925,6 +1226,8 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
             for (int j = 0; j < ndim; ++j) s->adim[s->da++] = (signed char)j;
     }
     s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + s->da;
+    s->update_every = 10;           // rebuild the decomposition every nlive / 10 iterations
+    if (const char *ue = getenv("NF_NS_UPDATE_EVERY")) s->update_every = atoi(ue) > 0 ? atoi(ue) : 10;
     A(cudaMallocHost((void **)&s->n_act_host, 2 * sizeof(int32_t)));
     A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -1037,16 +1340,30 @@ int nf_ns_run(nf_sampler *s)
         D.krun = s->krun; D.cand_off = s->cand_off;
         D.dims.da = s->da;
         std::memcpy(D.dims.adim, s->adim, sizeof(D.dims.adim));
+        D.dims.nfree = 0;
+        for (int j = 0; j < d; ++j) {
+            bool active = false;
+            for (int i = 0; i < s->da; ++i) active |= s->adim[i] == j;
+            if (!active) D.dims.fdim[D.dims.nfree++] = (signed char)j;
+        }
         D.K = K; D.Kmax = s->Kmax; D.d = d; D.nlive_max = NL; D.max_samples = s->cfg.max_samples; D.max_iter = s->cfg.max_iter;
         D.walks = s->walks; D.flags = s->cfg.flags; D.tol = s->cfg.tol; D.efr = s->cfg.efr; D.seed = s->cfg.seed;
         D.lock = lock;
         int64_t cand_ub = (int64_t)n_act * K + (s->Kmax > K ? (int64_t)s->cfg.target_batch : 0);
         if (cand_ub > s->cand_cap) cand_ub = s->cand_cap;
         if (prof) cudaEventRecord(pev[0], st);
-        ns_bounds_kernel<<<n_act, 128, 0, st>>>(s->act, s->n_act_dev, s->nlive, s->it, s->live_u, s->bound, NL, d,
-                                                s->cfg.efr, s->mode, s->coh_step, D.dims);
+        if (s->cfg.flags & 8)
+            ns_bounds_single_kernel<<<n_act, 128, 0, st>>>(s->act, s->n_act_dev, s->nlive, s->it, s->live_u, s->bound, NL, d,
+                                                           s->cfg.efr, s->mode, s->coh_step, D.dims);
+        else
+            ns_bounds_kernel<<<n_act, 128, (size_t)NL * sizeof(short), st>>>(s->act, s->n_act_dev, s->nlive, s->it, s->live_u,
+                                                                             s->bound, NL, d, s->cfg.efr, s->mode,
+                                                                             s->coh_step, D.dims, lock, s->update_every, 1);
         if (prof) cudaEventRecord(pev[1], st);
-        ns_propose_kernel<<<(unsigned)((s->Kmax + 127) / 128) * (unsigned)n_act, 128, 0, st>>>(D);
+        if (s->cfg.flags & 8)
+            ns_propose_kernel<false><<<(unsigned)((s->Kmax + 127) / 128) * (unsigned)n_act, 128, 0, st>>>(D);
+        else
+            ns_propose_kernel<true><<<(unsigned)((s->Kmax + 127) / 128) * (unsigned)n_act, 128, 0, st>>>(D);
         if (prof) cudaEventRecord(pev[2], st);
         // few vectors in flight (tail of a wave): smaller CTA tiles, so that the launch spreads over
         // more SMs and a lock-step's latency drops
@@ -1088,8 +1405,8 @@ int nf_ns_run(nf_sampler *s)
             cudaMemcpy(&ne, s->n_eval + r0, 8, cudaMemcpyDeviceToHost);
             cudaMemcpy(&z0, s->lnZ + r0, 8, cudaMemcpyDeviceToHost);
             cudaMemcpy(&lm, s->lmax + r0, 8, cudaMemcpyDeviceToHost);
-            std::vector<double> B((size_t)(d + d * d + 2));
-            cudaMemcpy(B.data(), s->bound + (size_t)r0 * (d + d * d + 2), B.size() * 8, cudaMemcpyDeviceToHost);
+            std::vector<double> B((size_t)ns_bound_stride(d));
+            cudaMemcpy(B.data(), s->bound + (size_t)r0 * ns_bound_stride(d), B.size() * 8, cudaMemcpyDeviceToHost);
             std::vector<double> cu((size_t)K * d);
             cudaMemcpy(cu.data(), s->cand_u, cu.size() * 8, cudaMemcpyDeviceToHost);   // slot 0 = first active run
             int valid = 0;
@@ -1097,9 +1414,10 @@ int nf_ns_run(nf_sampler *s)
             int32_t md = 0; double sc = 0;
             cudaMemcpy(&md, s->mode + r0, 4, cudaMemcpyDeviceToHost);
             cudaMemcpy(&sc, s->scale + r0, 8, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[ns] lock %d n_act %d run %d mode %d scale %.3g it %d evals %lld lnZ %.3f lmax %.3f cube %.0f lnV %.2f valid %d/%d diagL:",
-                    lock, n_act, r0, md, sc, it0, (long long)ne, z0, lm, B[d + d * d], B[d + d * d + 1], valid, K);
-            for (int j = 0; j < d; ++j) fprintf(stderr, " %.3g", B[d + j * d + j]);
+            const int da = s->da;
+            fprintf(stderr, "[ns] lock %d n_act %d run %d mode %d scale %.3g it %d evals %lld lnZ %.3f lmax %.3f cube %.0f ellipsoids %.0f lnV0 %.2f valid %d/%d diagL0:",
+                    lock, n_act, r0, md, sc, it0, (long long)ne, z0, lm, B[1], B[0], B[NS_BOUND_HDR + da + da * da], valid, K);
+            for (int j = 0; j < da; ++j) fprintf(stderr, " %.3g", B[NS_BOUND_HDR + da + j * da + j]);
             fprintf(stderr, "\n");
         }
     }

@@ -305,6 +305,8 @@ class CubeFitter:
             kw['walks'] = int(self.mn_kwargs['walks'])       # random-walk steps per new point
         if self.mn_kwargs.get('method'):
             kw['method'] = self.mn_kwargs['method']
+        if 'mmodal' in self.mn_kwargs:                       # MultiNest's switch (core.pyx:729): ellipsoid decomposition
+            kw['mmodal'] = bool(self.mn_kwargs['mmodal'])
         per_live = int(per_live or self.mn_kwargs.get('max_samples_per_live', 64))
         return NestedSamplingBatch(blk, self.utrans, ncomp, pix_ids=pix, nlive=nlive, tol=self.mn_kwargs['tol'],
                                    efr=self.mn_kwargs['efr'], n_prop=self.n_prop, seed=seed,

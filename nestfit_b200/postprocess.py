@@ -19,37 +19,30 @@ from .main import nans
 # ---------------------------------------------------------------------------
 # aggregation of per-pixel run groups into dense arrays (host side, numpy)
 # ---------------------------------------------------------------------------
+# dense map written to <dpath>/<name>  <-  (attribute of a run group, attribute holding the null-model value or None)
+RUN_ATTR_MAPS = {'evidence': ('global_lnZ', 'null_lnZ'), 'evidence_err': ('global_lnZ_err', None),
+                 'BIC': ('BIC', 'null_BIC'), 'AIC': ('AIC', 'null_AIC'), 'AICc': ('AICc', 'null_AICc')}
+
+
 def aggregate_run_attributes(store):
-    """'nbest' (b, l) and 'evidence', 'evidence_err', 'AIC', 'AICc', 'BIC' (m, b, l)
-    (main.py:664-721)."""
-    hdf, dpath = store.hdf, store.dpath
-    n_lon, n_lat = int(hdf.attrs['naxis1']), int(hdf.attrs['naxis2'])
-    ncomp_max = int(hdf.attrs['n_max_components'])
-    shape = (n_lon, n_lat, ncomp_max + 1)
-    lnz, lnzerr, bic, aic, aicc = (nans(shape) for _ in range(5))
-    nb = np.full((n_lon, n_lat), -1, dtype=np.int32)
-    for group in store.iter_pix_groups():
-        i_lon, i_lat = int(group.attrs['i_lon']), int(group.attrs['i_lat'])
-        nb[i_lon, i_lat] = group.attrs['nbest']
-        for model in group:
-            subg = group[model]
-            ncomp = int(subg.attrs['ncomp'])
-            if ncomp == 1:
-                lnz[i_lon, i_lat, 0] = subg.attrs['null_lnZ']
-                bic[i_lon, i_lat, 0] = subg.attrs['null_BIC']
-                aic[i_lon, i_lat, 0] = subg.attrs['null_AIC']
-                aicc[i_lon, i_lat, 0] = subg.attrs['null_AICc']
-            lnz[i_lon, i_lat, ncomp] = subg.attrs['global_lnZ']
-            lnzerr[i_lon, i_lat, ncomp] = subg.attrs['global_lnZ_err']
-            bic[i_lon, i_lat, ncomp] = subg.attrs['BIC']
-            aic[i_lon, i_lat, ncomp] = subg.attrs['AIC']
-            aicc[i_lon, i_lat, ncomp] = subg.attrs['AICc']
-    store.create_dataset('nbest', nb.transpose(), group=dpath)
-    store.create_dataset('evidence', lnz.transpose(), group=dpath)
-    store.create_dataset('evidence_err', lnzerr.transpose(), group=dpath)
-    store.create_dataset('BIC', bic.transpose(), group=dpath)
-    store.create_dataset('AIC', aic.transpose(), group=dpath)
-    store.create_dataset('AICc', aicc.transpose(), group=dpath)
+    """The per-run scalars of every pixel gathered into dense maps (main.py:664-721): 'nbest' (b, l) and one
+    (m, b, l) map per entry of RUN_ATTR_MAPS, plane 0 holding the null model's value where one exists."""
+    hdf = store.hdf
+    n_lon, n_lat, n_model = int(hdf.attrs['naxis1']), int(hdf.attrs['naxis2']), int(hdf.attrs['n_max_components']) + 1
+    maps = {name: nans((n_model, n_lat, n_lon)) for name in RUN_ATTR_MAPS}
+    nbest = np.full((n_lat, n_lon), -1, dtype=np.int32)
+    for pix in store.iter_pix_groups():
+        lon, lat = int(pix.attrs['i_lon']), int(pix.attrs['i_lat'])
+        nbest[lat, lon] = pix.attrs['nbest']
+        runs = [pix[key].attrs for key in pix]
+        for name, (attr, null_attr) in RUN_ATTR_MAPS.items():
+            for a in runs:
+                maps[name][int(a['ncomp']), lat, lon] = a[attr]
+            if null_attr is not None and runs:
+                maps[name][0, lat, lon] = runs[0][null_attr]       # every run of the pixel carries the same null value
+    store.create_dataset('nbest', nbest, group=store.dpath)
+    for name, arr in maps.items():
+        store.create_dataset(name, arr, group=store.dpath)
 
 
 def gaussian_kernel2d(sigma):
@@ -82,34 +75,27 @@ def convolve_nan_extend(img, kernel):
             num += w * vals[dy:dy + img.shape[0], dx:dx + img.shape[1]]
             den += w * good[dy:dy + img.shape[0], dx:dx + img.shape[1]]
     with np.errstate(invalid='ignore', divide='ignore'):
-        out = num / den * kernel.sum()
+        out = num / den          # astropy's default normalize_kernel=True: the kernel's own sum drops out
     out[den == 0] = np.nan
     return out
 
 
 def convolve_evidence(store, kernel):
-    """'conv_evidence' (m, b, l) and 'conv_nbest' (b, l) (main.py:724-774).  `kernel`:
-    2-D array or the standard deviation in pixels of a Gaussian kernel."""
-    if isinstance(kernel, (int, float)):
-        kernel = gaussian_kernel2d(float(kernel))
-    kernel = np.asarray(kernel, dtype=np.float64)
+    """'conv_evidence' (m, b, l): every evidence plane smoothed with `kernel` (a 2-D array, or the standard deviation
+    in pixels of a Gaussian), and 'conv_nbest' (b, l): the model selection redone on the smoothed planes
+    (main.py:724-774) -- the number of consecutive models whose smoothed evidence beats the previous one by the store's
+    threshold, at most one more than the number actually fitted at that position (no run exists beyond that)."""
+    kernel = _as_kernel(kernel)
     hdf, dpath = store.hdf, store.dpath
-    ncomp_max = int(hdf.attrs['n_max_components'])
-    lnZ_thresh = hdf.attrs['lnZ_threshold']
-    data = np.asarray(hdf[f'{dpath}/evidence'][...])
+    evidence = np.asarray(hdf[f'{dpath}/evidence'][...], dtype=np.float64)
     nbest = np.asarray(hdf[f'{dpath}/nbest'][...])
-    cdata = np.zeros_like(data)
-    for i in range(data.shape[0]):
-        cdata[i] = convolve_nan_extend(data[i], kernel)
-    conv_nbest = np.zeros(cdata[0].shape, dtype=np.int32)
-    for i in range(ncomp_max):
-        with np.errstate(invalid='ignore'):
-            conv_nbest[(conv_nbest == i) & (cdata[i + 1] - cdata[i] > lnZ_thresh)] += 1
-    conv_nbest[nbest == -1] = -1
-    overshot = conv_nbest - nbest >= 2       # a jump of +2 has no model run behind it
-    conv_nbest[overshot] = nbest[overshot] + 1
+    smooth = np.stack([convolve_nan_extend(plane, kernel) for plane in evidence])
+    with np.errstate(invalid='ignore'):
+        gains = np.diff(smooth, axis=0) > hdf.attrs['lnZ_threshold']          # NaN compares False
+    chain = np.cumprod(gains, axis=0).sum(axis=0).astype(np.int32)          # leading run of passed thresholds
+    conv_nbest = np.where(nbest == -1, -1, np.minimum(chain, nbest + 1)).astype(np.int32)
     store.create_dataset('conv_nbest', conv_nbest, group=dpath)
-    store.create_dataset('conv_evidence', cdata, group=dpath)
+    store.create_dataset('conv_evidence', smooth, group=dpath)
 
 
 def take_by_components(data, comps, axis=0, incl_zero=True):

@@ -31,13 +31,18 @@ class NestedSamplingBatch:
 
     def __init__(self, block, utrans, ncomp, pix_ids=None, nlive=100, tol=1.0, efr=0.3, n_prop=32, seed=1,
                  max_iter=1_000_000, max_samples=None, cold=False, lte=False, method='auto', walks=0,
-                 n_prop_max=None, target_batch=65536, keep_constant_dims=False):
+                 n_prop_max=None, target_batch=65536, keep_constant_dims=False, mmodal=False):
         """method: 'auto' = ellipsoidal rejection sampling that hands a run over to a
         constrained random walk once its acceptance stalls; 'ellipsoid' / 'rwalk' force one.
         walks: random-walk steps per new point (0 = 20 + number of dimensions the likelihood depends on).
         keep_constant_dims: keep the cube dimensions the priors overwrite (ConstantPrior rows, DuplicatePrior's
         second row) inside the bounding ellipsoid and the walk metric (the round-1 behaviour; default: they are
         drawn uniformly on their own).
+        mmodal: MultiNest-style decomposition of the live set into up to 8 ellipsoids for the rejection phase (the
+        reference runs MultiNest with mmodal=True, core.pyx:729); default False = one bounding ellipsoid rebuilt every
+        lock-step (measured on B200: the decomposition saves 12 % of the likelihood calls of a cube fit but its
+        clustering and overlap tests cost more than they save, and it raises ln Z by ~1-3 at 10-15 dimensions;
+        DESIGN.md section 4.4).
         n_prop_max / target_batch: once few runs are still active each gets up to n_prop_max
         proposals per lock-step (default 16 n_prop) so that a launch keeps ~target_batch vectors."""
         lib = _lib.load()
@@ -55,7 +60,7 @@ class NestedSamplingBatch:
             seed = int(np.random.SeedSequence().generate_state(1)[0])
         self.cfg = NsConfig(nlive_max=nlive_max, n_prop=int(n_prop), max_iter=int(min(max_iter, 2**31 - 1)),
                             max_samples=int(max_samples), bound_update_interval=int(walks),
-                            flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method] | (4 if keep_constant_dims else 0),
+                            flags={'auto': 0, 'rwalk': 1, 'ellipsoid': 2}[method] | (4 if keep_constant_dims else 0) | (0 if mmodal else 8),
                             tol=float(tol),
                             efr=float(efr), seed=int(seed),
                             n_prop_max=int(16 * n_prop if n_prop_max is None else n_prop_max),

@@ -83,11 +83,91 @@ def active_dims(packed_priors, n_model, ncomp):
     return act if act.size else np.arange(n_model * ncomp)
 
 
+NS_MAX_ELL = 8          # ellipsoids per run (nf_sampler.cu)
+NS_KMEANS_ITERS = 8
+
+
+def _ellipsoid(P, lnV_min):
+    """(mean, scaled lower Cholesky factor, ln V, index of the point of largest Mahalanobis radius) of the points P:
+    the covariance ellipsoid through the farthest point, enlarged to 1.2 x its volume and to at least lnV_min."""
+    n, d = P.shape
+    mean = P.mean(axis=0)
+    cov = (np.cov(P, rowvar=False).reshape(d, d) if n > 1 else np.zeros((d, d))) + 1e-12 * np.eye(d)
+    L = np.linalg.cholesky(cov)
+    y = np.linalg.solve(L, (P - mean).T)
+    r2 = (y * y).sum(axis=0)
+    far = int(np.argmax(r2))
+    f = max(float(r2[far]), 1e-300)
+    lndet = float(np.log(np.diag(L)).sum())
+    lnVd = 0.5 * d * math.log(math.pi) - math.lgamma(0.5 * d + 1.0)
+    lnV = max(lnVd + 0.5 * d * math.log(f) + lndet + math.log(1.2), lnV_min)
+    return mean, math.exp((lnV - lnVd - lndet) / d) * L, lnV, far
+
+
+def multi_ellipsoid_bound(U, lnX, nlive, efr):
+    """MultiNest-style decomposition of the live set into at most NS_MAX_ELL ellipsoids (ns_bounds_kernel):
+    breadth-first 2-means splits -- seeded at the point of largest Mahalanobis radius and the point farthest from
+    it, distances scaled by the parent's per-dimension spread -- kept when the children's volumes add up to less
+    than half the parent's, or when the parent is more than twice its share X n_c / (efr nlive) of the prior
+    volume and the children are smaller at all.  Returns a list of (mean, L, lnV)."""
+    lnpv = lnX - math.log(efr) - math.log(nlive)
+    d = U.shape[1]
+    minpts = d + 1
+    todo, done = [np.arange(U.shape[0])], []
+    while todo:
+        idx = todo.pop(0)
+        P = U[idx]
+        mean, L, lnV, far = _ellipsoid(P, math.log(idx.size) + lnpv)
+        if idx.size < 2 * minpts or len(todo) + len(done) + 2 > NS_MAX_ELL:
+            done.append((mean, L, lnV))
+            continue
+        w = 1.0 / np.maximum(P.std(axis=0), 1e-300)
+        c0 = P[far]
+        c1 = P[int(np.argmax((((P - c0) * w) ** 2).sum(axis=1)))]
+        for _ in range(NS_KMEANS_ITERS):
+            lab = (((P - c1) * w) ** 2).sum(axis=1) < (((P - c0) * w) ** 2).sum(axis=1)
+            if lab.all() or not lab.any():
+                break
+            c0, c1 = P[~lab].mean(axis=0), P[lab].mean(axis=0)
+        na, nb = int((~lab).sum()), int(lab.sum())
+        if na < minpts or nb < minpts:
+            done.append((mean, L, lnV))
+            continue
+        va = _ellipsoid(P[~lab], math.log(na) + lnpv)[2]
+        vb = _ellipsoid(P[lab], math.log(nb) + lnpv)[2]
+        lnsum = np.logaddexp(va, vb)
+        if lnsum < lnV + math.log(0.5) or (lnV > math.log(2.0) + math.log(idx.size) + lnpv and lnsum < lnV):
+            todo += [idx[~lab], idx[lab]]
+        else:
+            done.append((mean, L, lnV))
+    return done
+
+
+def sample_union(rng, ells, n):
+    """n points uniform in the union of the ellipsoids (pick one by volume, draw, keep with probability
+    1 / number of ellipsoids that contain the point)."""
+    lnV = np.array([e[2] for e in ells])
+    p = np.exp(lnV - lnV.max())
+    p /= p.sum()
+    d = ells[0][0].size
+    ks = rng.choice(len(ells), size=n, p=p)
+    X = np.empty((n, d))
+    for k in np.unique(ks):
+        m = ks == k
+        X[m] = ells[k][0] + _unit_ball(rng, int(m.sum()), d) @ ells[k][1].T
+    q = np.zeros(n)
+    for mean, L, _ in ells:
+        y = np.linalg.solve(L, (X - mean).T)
+        q += (y * y).sum(axis=0) <= 1.0
+    return X[rng.uniform(size=n) * q < 1.0]
+
+
 def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None, seed=0, max_iter=1_000_000,
-                    rwalk=False, active=None, return_samples=False):
+                    rwalk=False, active=None, return_samples=False, multi=False, update_every=10):
     """score(U[B, ndim]) -> lnL[B] (prior transform inside; NaN = not acceptable).
     `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk'); `active`: the dimensions
-    inside the ellipsoid / walk metric (default all).
+    inside the ellipsoid / walk metric (default all); `multi`: the MultiNest-style decomposition (the CUDA driver's
+    mmodal=True) instead of one ellipsoid rebuilt every step.
     Returns dict(lnZ, lnZ_err, max_loglike, n_iter, n_evals, n_samples); with `return_samples` also the dead
     points and final live points in death order: samples_u [n, ndim], samples_lnL [n], samples_lnw [n]
     (ln of the prior-mass weight; posterior weight = exp(lnL + lnw - lnZ))."""
@@ -129,13 +209,23 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
         return True
 
     mode, ea, ep, sc = (1 if rwalk else 0), 0, 0, 0.3
+    it_built, ells = 0, None
     while not st['done']:
-        mean, B, use_cube = _bound(U[:, act], st['it'], nlive, efr)
         if mode == 0:
+            lnX = -st['it'] / nlive
+            use_cube = lnX - math.log(efr) > math.log(0.5)
+            if multi and not use_cube and (ells is None or st['it'] - it_built >= nlive / update_every):
+                # the decomposition is rebuilt every nlive / update_every iterations; in between the ellipsoids stay
+                # valid (the constrained region only shrinks)
+                it_built = st['it']
+                ells = multi_ellipsoid_bound(U[:, act], lnX, nlive, efr)
+            if not multi:
+                mean, B, use_cube = _bound(U[:, act], st['it'], nlive, efr)
+                ells = [(mean, B, 0.0)]
             if use_cube:
                 cand = rng.uniform(size=(K, ndim))
             else:
-                ca = mean + _unit_ball(rng, K, d) @ B.T
+                ca = sample_union(rng, ells, K)
                 ca = ca[((ca > 0.0) & (ca < 1.0)).all(axis=1)]
                 cand = rng.uniform(size=(ca.shape[0], ndim))
                 cand[:, act] = ca
@@ -154,6 +244,7 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
                     mode, sc = 1, 0.3
                 ea = ep = 0
         else:
+            mean, B, _ = _bound(U[:, act], st['it'], nlive, efr)
             start = rng.integers(0, nlive, size=K)
             cu, cl = U[start].copy(), LL[start].copy()
             moved = np.zeros(K, dtype=bool)

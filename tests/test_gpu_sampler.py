@@ -215,7 +215,7 @@ def test_lnz_agrees_with_cpu_port(nb):
         out = orc.nh3_batch(xs, [1, 2], np.nan_to_num(th, nan=1.0), 1, data=data[None], noise=np.full((1, 2), 0.1))["lnL"]
         out[~np.isfinite(th).all(axis=1)] = np.nan
         return out
-    cpu = [ns_port.nested_sampling(score, 6, 200, tol=0.5, seed=s) for s in range(4)]
+    cpu = [ns_port.nested_sampling(score, 6, 200, tol=0.5, seed=s, active=ns_port.active_dims(packed, 6, 1)) for s in range(4)]
     # eight independent GPU runs of the same pixel in one batch (distinct Philox streams per run)
     ns = NestedSamplingBatch(blk, ut, 1, pix_ids=np.zeros(8, dtype=np.int32), nlive=200, tol=0.5, n_prop=32, seed=5)
     res = ns.run()

@@ -20,6 +20,7 @@ ap.add_argument('--no-posteriors', action='store_true')
 ap.add_argument('--walks', type=int, default=0)
 ap.add_argument('--method', default=None)
 ap.add_argument('--wave', type=int, default=16384)
+ap.add_argument('--mmodal', action='store_true', help='MultiNest-style ellipsoid decomposition')
 args = ap.parse_args()
 ut = nb.get_irdc_priors()
 n = args.size
@@ -36,6 +37,8 @@ if args.walks:
     mn['walks'] = args.walks
 if args.method:
     mn['method'] = args.method
+if args.mmodal:
+    mn['mmodal'] = True
 fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=args.ncomp_max, lnZ_thresh=11,
                        mn_kwargs=mn, nlive_snr_fact=5, n_prop=args.nprop, max_pixels_per_wave=args.wave,
                        n_streams=args.streams, pixels_per_stream=args.pps, store_posteriors=not args.no_posteriors)
