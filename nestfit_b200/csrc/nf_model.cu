@@ -5,12 +5,15 @@
 //   lanes <-> components during the FP64 set-up (window with the reference's floor rule),
 //   lanes <-> channels during the FP32 main loop: 128-channel chunks, lane l owns channels 128 g + l
 //   + {0, 32, 64, 96} (packed FP32x2 across channel pairs): most chunks are touched by one component, so
-//   four channels per lane spread the per-chunk work (ballot, bit walk, residual) over more terms.
+//   four channels per lane spread the per-chunk work (record fetch, residual) over more terms.
 // A CTA (8 warps) works on a tile of consecutive vectors; the pixel of the tile's first vector
 // is staged once in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).  Components
-// are unordered and have unequal widths, so the components touching a chunk are found by ballot;
-// only chunks some component touches are visited (bit walk over the union mask), the others
-// contribute their sum of d^2 from the per-pixel table built at upload (`d2chunk`).
+// are unordered and have unequal widths: per super-block of 32 chunks the (chunk, component) pairs that
+// overlap are compacted into a flat, channel-ordered work list (lanes <-> chunks: every lane collects the
+// components covering its chunk from the other lanes' chunk masks, a warp scan places its entries), and the
+// main loop walks that list -- one entry = one component on the lane's four channels of one chunk.  Chunks no
+// component touches are never visited: they contribute their sum of d^2 from the per-pixel table built at
+// upload (`d2chunk`).
 //
 // Reference arithmetic restated here (paths relative to the reference tree):
 //   c_gauss_predict      nestfit/models/gaussian.pyx:17-50 (__APPROX window rule 35-46)
@@ -36,14 +39,23 @@ struct __align__(32) GaussRec {
     float pad[3];
 };
 
+#define NF_GAUSS_LIST_CAP 256        // work-list entries resident per pass (the list is built in passes if longer)
+
 struct __align__(32) GaussScratch {
     GaussRec rec[NF_MAX_NCOMP_GAUSS];
+    uint2 list[NF_GAUSS_LIST_CAP];  // {record smem address | last-of-chunk << 31, float(first channel of the chunk)}
 };
 
 __device__ __forceinline__ float gauss_lds_f32(uint32_t addr)
 {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 gauss_lds64u(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ float4 gauss_lds128(uint32_t addr)
@@ -157,8 +169,10 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
         if (WRITE_PRED)       // chunks without components stay zero; the others are overwritten by the same lane
             for (int j = lane; j < a.n_chan; j += 32) prow[j] = 0.0f;
         float acc = 0.0f;
+        const uint32_t list_addr = smem_u32(sc.list);
+        const uint64_t l2a = pack2(lane_f, lane_f + 32.0f), l2b = pack2(lane_f + 64.0f, lane_f + 96.0f);
         for (int sb = 0; sb < nchunks; sb += 32) {
-            // chunks [sb, sb+32) touched by this lane's component, and by any component
+            // chunks [sb, sb+32) touched by this lane's component
             uint32_t cm = 0u;
             {
                 int c_lo = (lo >> 7) - sb, c_hi = ((hi - 1) >> 7) - sb;
@@ -168,32 +182,56 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
                     cm = (0xffffffffu >> (31 - c_hi)) & (0xffffffffu << c_lo);
                 }
             }
-            uint32_t un = __reduce_or_sync(NF_FULL, cm);
+            // lanes <-> chunks: the components covering chunk sb + lane (bit c = component c)
+            uint32_t mine = 0u;
+            for (int c = 0; c < ncomp; ++c) mine |= ((__shfl_sync(NF_FULL, cm, c) >> lane) & 1u) << c;
+            const int n_mine = __popc(mine);
             if (have_data) {          // a chunk no component touches contributes its sum of d^2
                 const int g = sb + lane;
-                if (g < nchunks && !((un >> lane) & 1u)) {
+                if (g < nchunks && n_mine == 0) {
                     const float4 q = __ldg(reinterpret_cast<const float4 *>(a.d2chunk + pix * (int64_t)(a.n_pad >> 5)) + g);
                     acc += (q.x + q.y) + (q.z + q.w);
                 }
             }
-            // touched chunks in ascending order: windows are wide, so nearly every chunk between the first
-            // and the last touched one is visited and a plain scan beats a find-first-set walk
-            int cc = un ? __ffs(un) - 1 : 32;
-            float xa = (float)((sb + cc) << 7) + lane_f;
-            for (uint32_t rest = un >> (cc & 31); cc < 32 && rest; ++cc, rest >>= 1, xa += 128.0f) {
-                if (!(rest & 1u)) continue;
-                uint32_t lm = __ballot_sync(NF_FULL, (cm >> cc) & 1u);
-                const int j0 = (sb + cc) << 7;
-                const uint64_t x2a = pack2(xa, xa + 32.0f), x2b = pack2(xa + 64.0f, xa + 96.0f);
-                float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-                while (lm) {          // components are unordered: walk the set bits
-                    const uint32_t lsb = lm & (0u - lm);
-                    lm ^= lsb;
-                    const uint32_t ra = rec_addr + g_lsb_rec_off[(lsb * 0x077CB531u) >> 27];
+            int incl = n_mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(NF_FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int n_tot = __shfl_sync(NF_FULL, incl, 31);
+            const int first = incl - n_mine;                  // position of this chunk's first entry
+            const uint32_t xbits = __float_as_uint((float)((sb + lane) << 7));
+            float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+            // the list is consumed in passes of NF_GAUSS_LIST_CAP entries (one pass unless > 8 components overlap
+            // everywhere); a chunk's entries may straddle two passes: the model sums m0..m3 carry over
+            for (int p0 = 0; p0 < n_tot; p0 += NF_GAUSS_LIST_CAP) {
+                __syncwarp();
+                {
+                    uint32_t rest = mine;
+                    int at = first - p0;
+                    while (rest) {
+                        const uint32_t lsb = rest & (0u - rest);
+                        rest ^= lsb;
+                        if (at >= 0 && at < NF_GAUSS_LIST_CAP)
+                            sc.list[at] = make_uint2((rec_addr + g_lsb_rec_off[(lsb * 0x077CB531u) >> 27]) |
+                                                     (rest == 0u ? 0x80000000u : 0u), xbits);
+                        ++at;
+                    }
+                }
+                __syncwarp();
+                const int n_here = min(n_tot - p0, NF_GAUSS_LIST_CAP);
+                uint32_t sa = list_addr;
+                const uint32_t send = sa + (uint32_t)n_here * 8u;
+#pragma unroll 1
+                for (; sa != send; sa += 8u) {
+                    const uint2 ent = gauss_lds64u(sa);
+                    const uint32_t ra = ent.x & 0x7fffffffu;
                     const float4 A = gauss_lds128(ra);
                     const float h = gauss_lds_f32(ra + 16);
-                    const uint64_t R2 = pack2(A.x, A.x), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z);
-                    const uint64_t da2 = add2(x2a, R2), db2 = add2(x2b, R2);       // exact: multiples of 1/2
+                    const float s0 = __uint_as_float(ent.y) + A.x;                     // chunk base - R' (exact)
+                    const uint64_t S2 = pack2(s0, s0), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z);
+                    const uint64_t da2 = add2(l2a, S2), db2 = add2(l2b, S2);          // exact: multiples of 1/2
                     const uint64_t ta2 = fma2(K2, da2, B2), tb2 = fma2(K2, db2, B2);
                     float d0, d1, d2, d3, e0, e1, e2, e3;
                     unpack2(da2, d0, d1);
@@ -208,30 +246,34 @@ nf_gauss_kernel(const __grid_constant__ NfLikeArgs a)
                     if (fabsf(d1) <= h) m1 = fmaf(A.w, e1, m1);
                     if (fabsf(d2) <= h) m2 = fmaf(A.w, e2, m2);
                     if (fabsf(d3) <= h) m3 = fmaf(A.w, e3, m3);
-                }
-                if (WRITE_PRED) {
-                    const int j = j0 + lane;
-                    if (j < a.n_chan) prow[j] = m0;
-                    if (j + 32 < a.n_chan) prow[j + 32] = m1;
-                    if (j + 64 < a.n_chan) prow[j + 64] = m2;
-                    if (j + 96 < a.n_chan) prow[j + 96] = m3;
-                } else {
-                    float q0, q1, q2, q3;
-                    if (staged) {
-                        const uint32_t sa = srow + (uint32_t)j0 * 4u;
-                        q0 = gauss_lds_f32(sa);
-                        q1 = gauss_lds_f32(sa + 128u);
-                        q2 = gauss_lds_f32(sa + 256u);
-                        q3 = gauss_lds_f32(sa + 384u);
-                    } else {
-                        const float4 q = gauss_row4_global(grow + j0);
-                        q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
+                    if ((int)ent.x < 0) {            // last component of this chunk: residual
+                        const int j0 = (int)__uint_as_float(ent.y);
+                        if (WRITE_PRED) {
+                            const int j = j0 + lane;
+                            if (j < a.n_chan) prow[j] = m0;
+                            if (j + 32 < a.n_chan) prow[j + 32] = m1;
+                            if (j + 64 < a.n_chan) prow[j + 64] = m2;
+                            if (j + 96 < a.n_chan) prow[j + 96] = m3;
+                        } else {
+                            float q0, q1, q2, q3;
+                            if (staged) {
+                                const uint32_t da = srow + (uint32_t)j0 * 4u;
+                                q0 = gauss_lds_f32(da);
+                                q1 = gauss_lds_f32(da + 128u);
+                                q2 = gauss_lds_f32(da + 256u);
+                                q3 = gauss_lds_f32(da + 384u);
+                            } else {
+                                const float4 q = gauss_row4_global(grow + j0);
+                                q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
+                            }
+                            q0 -= m0; q1 -= m1; q2 -= m2; q3 -= m3;
+                            acc = fmaf(q0, q0, acc);
+                            acc = fmaf(q1, q1, acc);
+                            acc = fmaf(q2, q2, acc);
+                            acc = fmaf(q3, q3, acc);
+                        }
+                        m0 = 0.0f; m1 = 0.0f; m2 = 0.0f; m3 = 0.0f;
                     }
-                    q0 -= m0; q1 -= m1; q2 -= m2; q3 -= m3;
-                    acc = fmaf(q0, q0, acc);
-                    acc = fmaf(q1, q1, acc);
-                    acc = fmaf(q2, q2, acc);
-                    acc = fmaf(q3, q3, acc);
                 }
             }
         }

@@ -75,7 +75,7 @@ struct nf_sampler {
     int32_t *mode, *coh_step, *coh_acc, *eff_acc, *eff_prop, *chain_moved;
     double *lstar, *scale, *chain_u, *chain_th, *chain_l;
     int walks;
-    int update_every;                  // a run's ellipsoid decomposition is rebuilt every nlive / update_every iterations
+    int update_every;                  // lock-steps between rebuilds of a run's ellipsoid decomposition (mmodal)
     int da;                            // dimensions the likelihood depends on (the others are constant / duplicated)
     signed char adim[NS_MAX_DIM];      // their indices in the unit-cube vector
     int32_t *n_act_host;               // pinned: {n_act, n_cand}
@@ -442,11 +442,10 @@ ns_bounds_kernel(const int32_t *act, const int32_t *n_act_dev, const int32_t *nl
         if (tid == 0) { B[0] = 0.0; B[1] = 1.0; B[2] = -1.0e30; }
         return;
     }
-    // the decomposition is rebuilt every nlive / update_every iterations of the run (MultiNest rebuilds when the
-    // prior volume has shrunk by a set factor); in between the ellipsoids stay valid supersets, the constrained
-    // region only shrinks
+    // the decomposition is rebuilt every `update_every` lock-steps; in between the ellipsoids stay valid supersets
+    // (the constrained region only shrinks)
     const int it_now = it_arr[r];
-    if (!walk && B[1] < 0.5 && B[0] >= 1.0 && (double)it_now - B[2] < (double)nl / (double)update_every) return;
+    if (!walk && B[1] < 0.5 && B[0] >= 1.0 && (lock % update_every) != 0) return;
     const double *U = live_u + (int64_t)r * nlive_max * ds;
     const double lnpv = walk ? -INFINITY : lnX - log(efr) - log((double)nl);
     const int64_t es = ns_ell_stride(ndim);
@@ -1226,8 +1225,8 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
             for (int j = 0; j < ndim; ++j) s->adim[s->da++] = (signed char)j;
     }
     s->walks = cfg->bound_update_interval > 1 ? cfg->bound_update_interval : 20 + s->da;
-    s->update_every = 10;           // rebuild the decomposition every nlive / 10 iterations
-    if (const char *ue = getenv("NF_NS_UPDATE_EVERY")) s->update_every = atoi(ue) > 0 ? atoi(ue) : 10;
+    s->update_every = 8;            // lock-steps between rebuilds of the decomposition (mmodal)
+    if (const char *ue = getenv("NF_NS_UPDATE_EVERY")) s->update_every = atoi(ue) > 0 ? atoi(ue) : 8;
     A(cudaMallocHost((void **)&s->n_act_host, 2 * sizeof(int32_t)));
     A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);

@@ -163,7 +163,7 @@ def sample_union(rng, ells, n):
 
 
 def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None, seed=0, max_iter=1_000_000,
-                    rwalk=False, active=None, return_samples=False, multi=False, update_every=10):
+                    rwalk=False, active=None, return_samples=False, multi=False, update_every=8):
     """score(U[B, ndim]) -> lnL[B] (prior transform inside; NaN = not acceptable).
     `rwalk=True` starts with the random walk (the CUDA driver's method='rwalk'); `active`: the dimensions
     inside the ellipsoid / walk metric (default all); `multi`: the MultiNest-style decomposition (the CUDA driver's
@@ -209,19 +209,19 @@ def nested_sampling(score, ndim, nlive, tol=1.0, efr=0.3, n_prop=32, walks=None,
         return True
 
     mode, ea, ep, sc = (1 if rwalk else 0), 0, 0, 0.3
-    it_built, ells = 0, None
+    step, ells = 0, None
     while not st['done']:
         if mode == 0:
             lnX = -st['it'] / nlive
             use_cube = lnX - math.log(efr) > math.log(0.5)
-            if multi and not use_cube and (ells is None or st['it'] - it_built >= nlive / update_every):
-                # the decomposition is rebuilt every nlive / update_every iterations; in between the ellipsoids stay
-                # valid (the constrained region only shrinks)
-                it_built = st['it']
+            if multi and not use_cube and (ells is None or step % update_every == 0):
+                # the decomposition is rebuilt every `update_every` lock-steps; in between the ellipsoids stay valid
+                # (the constrained region only shrinks)
                 ells = multi_ellipsoid_bound(U[:, act], lnX, nlive, efr)
             if not multi:
                 mean, B, use_cube = _bound(U[:, act], st['it'], nlive, efr)
                 ells = [(mean, B, 0.0)]
+            step += 1
             if use_cube:
                 cand = rng.uniform(size=(K, ndim))
             else:
