@@ -17,7 +17,7 @@ def nh3_counts():
 
 
 def gauss_count():
-    B, n_chan, ncomp = 1 << 18, 4096, 8
+    B, n_chan, ncomp = 1 << 20, 4096, 8
     rng = np.random.default_rng(5)
     v = (np.arange(n_chan) - 2047.5) * 0.05
     x = np.sort(bench.NU_NH3[0] * (1 - v / bench.CKMS))
