@@ -484,7 +484,8 @@ def _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag):
     return nb.CubeStack(cubes), ut, ncomp_map, shm
 
 
-def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, tag, blocks_per_gpu, posteriors=True):
+def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, tag, blocks_per_gpu, posteriors=True,
+              concurrent_blocks=4):
     """One cube-fit leg through the public API: `CubeFitter.fit_cube` at N = 1, its SPMD form `fit_cube_rank` (one
     existing process per GPU, blocks claimed dynamically, one store chunk per rank) at N > 1.  The timed region
     holds everything the call does: store creation, uploads, the fit, the posterior products, the chunk writes."""
@@ -510,11 +511,11 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
         results = fitter.fit_cube(str(store_root / "cube"), nproc=1, devices=[dev])
     else:
         results = fitter.fit_cube_rank(str(store_root / "cube"), rank, world, blocks_per_gpu=blocks_per_gpu, device=dev,
-                                       barrier=barrier)
+                                       barrier=barrier, concurrent_blocks=concurrent_blocks)
     barrier()
     wall = time.perf_counter() - t0
     # per-rank bookkeeping -> rank 0
-    mine = {"busy_s": float(sum(r["seconds"] for r in results)), "n_evals": int(sum(r["n_evals"] for r in results)),
+    mine = {"busy_s": float(fitter.stats.get("rank_fit_seconds", sum(r["seconds"] for r in results))), "n_evals": int(sum(r["n_evals"] for r in results)),
             "n_pix": int(sum(np.asarray(r["nbest"]).size for r in results)), "blocks": len(results),
             "store_s": float(sum(r.get("store_seconds", 0.0) for r in results)),
             "store_wait_s": float(sum(r.get("store_wait_seconds", 0.0) for r in results)),
@@ -543,7 +544,8 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
                "ncomp_max": ncomp_max, "noise": "0.05..0.3 K gradient (NoiseMap)" if noise_grad else "0.1 K uniform",
                "nlive": "100 + 5*SNR", "tol": 1.0, "lnZ_thresh": 11, "blocks_per_gpu": blocks_per_gpu if world > 1 else 1,
                "api": "CubeFitter.fit_cube(store, nproc=1)" if world == 1 else
-                      f"CubeFitter.fit_cube_rank(store, rank, {world}, blocks_per_gpu={blocks_per_gpu})",
+                      f"CubeFitter.fit_cube_rank(store, rank, {world}, blocks_per_gpu={blocks_per_gpu}, "
+                      f"concurrent_blocks={concurrent_blocks})",
                "likelihood_evals_per_pixel": sum(p["n_evals"] for p in per_rank) / n_pix,
                "likelihood_evals_by_ncomp": np.sum([p["evals_by_ncomp"] for p in per_rank], axis=0).tolist(),
                "nbest_matches_truth": float((np.minimum(nbest_local, ncomp_max) == ncomp_map).mean()),
@@ -578,7 +580,8 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
                 out["cpu_baseline"] = cube_cpu_baseline(aux[0], aux[1], (args.cube_size, args.cube_size), aux[2])
             legs["cube_fit_config2"] = out
     if sx > 0:
-        out, _ = _cube_leg(nb, (sx, sy), 4, True, 78, rank, world, dev, dist, "c3", args.blocks_per_gpu)
+        out, _ = _cube_leg(nb, (sx, sy), 4, True, 78, rank, world, dev, dist, "c3", args.blocks_per_gpu,
+                           concurrent_blocks=args.concurrent_blocks)
         if rank == 0:
             out["metric"] = "cube pixels/s fit (configs[3] shape: ncomp <= 4, noise map; one fixed cube over N GPUs)"
             out["scaling"] = "strong"
@@ -587,7 +590,7 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
         # the posterior rows of 262 144 pixels are ~400 GB: this leg stores everything but them (attributes,
         # marginals, best-fit / MAP vectors); the two smaller legs store the posteriors as well
         out, _ = _cube_leg(nb, (512, 512), 4, True, 79, rank, world, dev, dist, "c3full", args.blocks_per_gpu,
-                           posteriors=False)
+                           posteriors=False, concurrent_blocks=args.concurrent_blocks)
         if rank == 0:
             out["metric"] = "cube pixels/s fit (configs[3]: 512x512, ncomp <= 4, noise map)"
             out["scaling"] = "strong"
@@ -785,6 +788,7 @@ def main():
                     help="LONxLAT of the fixed configs[3]-shaped cube fitted at every N (strong scaling; 0x0 = skip)")
     ap.add_argument("--full-cube", action="store_true", help="also fit the full 512x512 configs[3] cube (default at N = 8)")
     ap.add_argument("--blocks-per-gpu", type=int, default=8, help="over-decomposition of the multi-GPU cube fit")
+    ap.add_argument("--concurrent-blocks", type=int, default=4, help="blocks a rank keeps in flight (host threads / streams)")
     args = ap.parse_args()
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch one process per GPU (the driver does this itself)

@@ -595,11 +595,15 @@ class CubeFitter:
         self.stats['results'] = results
         return results
 
-    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None):
+    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None, concurrent_blocks=4):
         """SPMD form of `fit_cube` for processes that already exist, one per GPU (torchrun): every rank calls this
         with its `rank`; blocks are claimed through the store directory (exclusive file creation), rank 0 creates
         the store and links the chunks at the end.  `barrier()` (e.g. torch.distributed.barrier) separates
-        creation, fitting and linking.  Returns this rank's list of per-block results."""
+        creation, fitting and linking.  A rank keeps `concurrent_blocks` blocks in flight, each fitted by its own
+        host thread on its own CUDA stream: the blocks of an over-decomposed cube are small, and one small block
+        alone leaves the GPU underfilled (fewer runs per lock-step than the device has warps, and a thin tail per
+        wave); several in flight fill it while the claims keep the ranks balanced.
+        Returns this rank's list of per-block results."""
         self._check_partition(world, blocks_per_gpu, list(range(world)))
         barrier = barrier or (lambda: None)
         if rank == 0:
@@ -613,20 +617,59 @@ class CubeFitter:
         claims = store_dir / 'claims'
         claims.mkdir(exist_ok=True)
         sink = chunk_sink(store_dir, rank, self.store_posteriors)
-        results = []
-        # static start (block j of the first `world` goes to rank j), then whatever is still unclaimed
-        order = [rank] + [j for j in range(len(indices)) if j != rank] if rank < len(indices) else range(len(indices))
-        try:
-            for j in order:
+        if self.utrans is not None and hasattr(self.utrans, 'handle'):
+            self.utrans.handle(device)              # the device prior plan exists before the threads start
+        # every rank starts at its own stretch of the block list and wraps around: contiguous blocks per rank
+        # while the load is even, anything unclaimed once a rank runs out of its own
+        first = (rank * len(indices)) // world
+        order = [(first + k) % len(indices) for k in range(len(indices))]
+        results, errors, lock = [], [], threading.Lock()
+        cursor = [0]
+
+        def claim():
+            while True:
+                with lock:
+                    if errors or cursor[0] >= len(order):
+                        return None
+                    j = order[cursor[0]]
+                    cursor[0] += 1
                 try:
                     os.close(os.open(claims / f'block{j}', os.O_CREAT | os.O_EXCL | os.O_WRONLY))
+                    return j
                 except FileExistsError:
                     continue
-                res = self.fit_block(indices[j], device=device, group_root=sink)
-                res['block'] = j
-                results.append(res)
+
+        def worker():
+            while True:
+                j = claim()
+                if j is None:
+                    return
+                try:
+                    res = self.fit_block(indices[j], device=device, group_root=sink)
+                    res['block'] = j
+                    with lock:
+                        results.append(res)
+                except BaseException as exc:        # re-raised in the caller's thread
+                    with lock:
+                        errors.append(exc)
+                    return
+
+        n_thr = max(1, min(int(concurrent_blocks), len(indices)))
+        t0 = time.perf_counter()
+        try:
+            if n_thr == 1:
+                worker()
+            else:
+                threads = [threading.Thread(target=worker) for _ in range(n_thr)]
+                for th in threads:
+                    th.start()
+                for th in threads:
+                    th.join()
         finally:
             sink.close()
+        if errors:
+            raise errors[0]
+        self.stats['rank_fit_seconds'] = time.perf_counter() - t0
         barrier()
         if rank == 0:
             with HdfStore(store_name) as store:

@@ -15,6 +15,7 @@ the store: its posterior rows arrive as one float32 pool with run offsets, its a
 """
 import inspect
 import json
+import threading
 import warnings
 from collections.abc import Mapping
 from pathlib import Path
@@ -333,6 +334,7 @@ class SlabSink:
         self._seq = len(list(self.dir.glob('w*_n*.npz')))
         self._pseq = len(list(self.dir.glob('pix_*.npz')))
         self._groups = None
+        self._lock = threading.Lock()           # several blocks of one rank may write concurrently
 
     def _group_root(self):
         if self._groups is None:
@@ -341,18 +343,21 @@ class SlabSink:
         return self._groups
 
     def require_group(self, path):
-        return self._group_root().require_group(path)
+        with self._lock:                        # creation of the intermediate groups is check-then-insert
+            return self._group_root().require_group(path)
 
     def create_group(self, path):
-        return self._group_root().create_group(path)
+        with self._lock:
+            return self._group_root().create_group(path)
 
     @property
     def attrs(self):
         return self._group_root().attrs
 
     def add_wave(self, wave):
-        stem = self.dir / f'w{self._seq:05d}_n{wave.ncomp}'
-        self._seq += 1
+        with self._lock:
+            stem = self.dir / f'w{self._seq:05d}_n{wave.ncomp}'
+            self._seq += 1
         have_post = self.store_posteriors and wave.posteriors is not None
         if have_post:
             np.save(f'{stem}.post.npy', wave.posteriors)
@@ -361,9 +366,11 @@ class SlabSink:
                  bestfit=wave.bestfit, mapfit=wave.mapfit, **{f'col_{k}': v for k, v in wave.columns.items()})
 
     def add_pixels(self, i_lon, i_lat, nbest):
-        np.savez(self.dir / f'pix_{self._pseq:05d}.npz', i_lon=np.asarray(i_lon, dtype=np.int64),
-                 i_lat=np.asarray(i_lat, dtype=np.int64), nbest=np.asarray(nbest, dtype=np.int64))
-        self._pseq += 1
+        with self._lock:
+            path = self.dir / f'pix_{self._pseq:05d}.npz'
+            self._pseq += 1
+        np.savez(path, i_lon=np.asarray(i_lon, dtype=np.int64), i_lat=np.asarray(i_lat, dtype=np.int64),
+                 nbest=np.asarray(nbest, dtype=np.int64))
 
     def close(self):
         if self._groups is not None:

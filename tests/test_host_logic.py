@@ -155,8 +155,10 @@ def test_cubefitter_pickles_for_spawned_workers(nb):
     x = [velocity_axis_hz(1, 100, 0.3), velocity_axis_hz(2, 100, 0.3)]
     stack = CubeStack([DataCube.from_arrays(np.zeros((2, 2, 100)), x[t], 0.1, trans_id=t + 1) for t in range(2)])
     fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=2)
+    fitter._store, fitter._device = open(__file__), 3      # an open store (unpicklable) and a device binding: left behind
     try:
         clone = pickle.loads(pickle.dumps(fitter))
+        assert not hasattr(clone, '_store') and not hasattr(clone, '_device')
     finally:
         ut._handles = {}
     assert clone.utrans._handles == {} and clone.utrans.n_param == 6 and clone.ncomp_max == 2
@@ -333,3 +335,76 @@ def test_fit_cube_rank_spmd_claims(tmp_path, monkeypatch, nb):
     assert sorted((g.attrs['i_lon'], g.attrs['i_lat']) for g in groups) == [(i, j) for i in range(6) for j in range(5)]
     assert {g.attrs['nbest'] for g in groups} == {0, 1, 2}                         # written by all three ranks
     store.close()
+
+
+def test_slab_store_wave_round_trip(tmp_path, nb):
+    """A finished wave (posterior pool + run offsets + attribute columns) written as a slab and read back through
+    the reference's tree: /pix/<lon>/<lat>/<ncomp> groups with the dumper's attributes and datasets, lazily
+    materialised; a later wave of the same (pixel, ncomp) replaces the earlier run; chunks are linked on demand."""
+    from nestfit_b200.store import HdfStore, Wave, run_attr_columns, RUN_ATTR_COLUMNS, MARG_COLS
+    rng = np.random.default_rng(4)
+    ndim, n_run = 6, 3
+    n_s = np.array([5, 9, 4])
+    off = np.concatenate([[0], np.cumsum(n_s)])
+    post = rng.normal(size=(off[-1], ndim + 2)).astype(np.float32)
+    res = dict(lnZ=np.array([-10.0, -20.0, -30.0]), lnZ_err=np.full(3, 0.1), max_loglike=np.array([-5.0, -6.0, -7.0]),
+               n_iter=np.array([100, 200, 300]), n_evals=np.array([1000, 2000, 3000]), truncated=np.zeros(3, bool))
+    cols = run_attr_columns(ndim, 760, [50, 60, 70], [-100.0, -110.0, -120.0], res, n_s)
+    assert tuple(cols) == RUN_ATTR_COLUMNS
+    wave = Wave(1, ndim, 760, [0, 0, 2], [1, 3, 1], cols, off, post, rng.normal(size=(n_run, 15, ndim)),
+                rng.normal(size=(n_run, ndim)), rng.normal(size=(n_run, ndim)))
+    store = HdfStore(str(tmp_path / 'slab'), nchunks=2)
+    sink = store.chunk_sink(1)
+    sink.add_wave(wave)
+    sink.add_pixels([0, 0, 2], [1, 3, 1], [1, 0, 1])
+    # the repeat of pixel (0, 3): a second wave with one run
+    cols2 = {k: v[1:2].copy() for k, v in cols.items()}
+    cols2['global_lnZ'][:] = -19.0
+    sink.add_wave(Wave(1, ndim, 760, [0], [3], cols2, [0, 2], post[:2], wave.marginals[1:2], wave.bestfit[1:2], wave.mapfit[1:2]))
+    sink.close()
+    store.link_files()
+    groups = list(store.iter_pix_groups())
+    assert sorted((g.attrs['i_lon'], g.attrs['i_lat'], g.attrs['nbest']) for g in groups) == [(0, 1, 1), (0, 3, 0), (2, 1, 1)]
+    run = store.hdf['/pix/2/1/1']
+    assert run.attrs['ncomp'] == 1 and run.attrs['n_params'] == ndim and run.attrs['n_samples'] == 4
+    assert run.attrs['global_lnZ'] == -30.0 and run.attrs['n_live'] == 70 and list(run.attrs['marg_cols']) == MARG_COLS
+    assert isinstance(run.attrs['n_samples'], int) and isinstance(run.attrs['BIC'], float)
+    np.testing.assert_array_equal(run['posteriors'], post[off[2]:off[3]])
+    np.testing.assert_array_equal(run['marginals'], wave.marginals[2])
+    np.testing.assert_array_equal(run['bestfit_params'], wave.bestfit[2])
+    assert store.hdf['/pix/0/3/1'].attrs['global_lnZ'] == -19.0 and store.hdf['/pix/0/3/1']['posteriors'].shape == (2, ndim + 2)
+    assert store.find_first_valid_group().attrs['ncomp'] == 1
+    store.close()
+    again = HdfStore(str(tmp_path / 'slab'))          # linked state persists; the view is rebuilt from the slabs
+    assert again.nchunks == 2 and len(list(again.iter_pix_groups())) == 3
+    again.reset_pix_links()
+    assert '/pix' not in again.hdf
+    again.close()
+
+
+def test_noise_maps_and_pbimg(nb):
+    """NoiseMap keeps the image in (lon, lat) order and answers scalar and array indices; from_pbimg takes the plane of
+    a 2-, 3- or 4-axis primary-beam image (main.py:39-65)."""
+    img = np.arange(12.0).reshape(3, 4)                 # (lat, lon)
+    nm = nb.NoiseMap(img)
+    assert nm.shape == (4, 3) and nm.get_noise(2, 1) == img[1, 2]
+    np.testing.assert_array_equal(nm.get_noise(np.array([0, 3]), np.array([2, 0])), [img[2, 0], img[0, 3]])
+    pb = np.ones((1, 1, 3, 4)); pb[0, 0, 1, 2] = 0.5; pb[0, 0, 0, 0] = 0.0
+    m = nb.NoiseMap.from_pbimg(0.1, pb)
+    assert m.get_noise(2, 1) == pytest.approx(0.2) and np.isinf(m.get_noise(0, 0)) and m.get_noise(3, 2) == pytest.approx(0.1)
+    assert nb.NoiseMap.from_pbimg(0.1, pb[0]).shape == (4, 3) and nb.NoiseMap.from_pbimg(0.1, pb[0, 0]).shape == (4, 3)
+    with pytest.raises(ValueError, match='Cannot parse shape'):
+        nb.NoiseMap.from_pbimg(0.1, np.ones(5))
+    assert nb.NoiseMapUniform(0.3).shape is None
+
+
+def test_convolve_nan_extend_ignores_kernel_sum(nb):
+    """astropy's convolve(..., boundary='extend') normalises the kernel (normalize_kernel=True): an unnormalised
+    kernel gives the same map (the conv_nbest threshold test must not scale with the kernel's sum)."""
+    from nestfit_b200.postprocess import convolve_nan_extend, gaussian_kernel2d
+    rng = np.random.default_rng(1)
+    img = rng.normal(size=(9, 7)); img[2, 3] = np.nan
+    k = gaussian_kernel2d(1.0)
+    np.testing.assert_allclose(convolve_nan_extend(img, 7.5 * k), convolve_nan_extend(img, k), rtol=1e-13)
+    assert np.isfinite(convolve_nan_extend(img, k)).all()                      # the NaN is interpolated over
+    np.testing.assert_allclose(convolve_nan_extend(np.full((5, 5), 3.0), k), 3.0, rtol=1e-13)
