@@ -3,11 +3,28 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "nf_internal.cuh"
 #include "../../include/nf_nh3_tables.h"
 #include "../../include/nf_n2hp_tables.h"
+
+cudaError_t nf_ensure_dyn_smem(const void *func, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = limit[std::make_pair(device, func)];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 thread_local double g_nf_last_kernel_ms = 0.0;
 thread_local int64_t g_nf_last_launches = 0;

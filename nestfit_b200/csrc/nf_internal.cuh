@@ -107,5 +107,9 @@ cudaError_t nf_launch_pack_rows(const void *src, int src_f64, float *dst, int64_
 cudaError_t nf_launch_prior_transform(const nf_priors *pr, double *u, int64_t B, int ncomp,
                                       cudaStream_t st, const int32_t *B_dev = nullptr);
 
+// The dynamic shared-memory limit of a kernel is state of the (device, function) pair, shared by all host threads:
+// raise it monotonically under a lock (a thread that lowered it would fail the launches of another).  nf_capi.cu
+cudaError_t nf_ensure_dyn_smem(const void *func, size_t bytes);
+
 extern thread_local double g_nf_last_kernel_ms;
 extern thread_local int64_t g_nf_last_launches;

@@ -293,7 +293,7 @@ static cudaError_t gauss_launch_one(const NfLikeArgs &a, cudaStream_t st)
     auto kern = nf_gauss_kernel<WP, PT>;
     const size_t smem = 128 + (((size_t)a.n_pad * 4 + 127) / 128) * 128 + sizeof(GaussScratch) * NF_WARPS_PER_CTA;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = nf_ensure_dyn_smem((const void *)kern, smem);
     if (e) return e;
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t grid = (a.B + tile - 1) / tile;

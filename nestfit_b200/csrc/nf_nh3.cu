@@ -665,7 +665,7 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     auto kern = nf_nh3_kernel<MODEL, NC, WP, PT>;
     const size_t smem = nh3_smem_bytes<NC>(a);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = nf_ensure_dyn_smem((const void *)kern, smem);
     if (e) return e;
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t grid = (a.B + tile - 1) / tile;

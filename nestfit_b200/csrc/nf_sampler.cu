@@ -1312,7 +1312,7 @@ int nf_ns_run(nf_sampler *s)
     // sizes grids from upper bounds -- the active list only shrinks and the candidate total is
     // at most n_act K + target -- and reads the counts back every `sync_every` lock-steps.
     const size_t upd_smem = (size_t)4 * NL * sizeof(double);
-    if (cudaFuncSetAttribute(ns_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem) != cudaSuccess)
+    if (nf_ensure_dyn_smem((const void *)ns_update_kernel, upd_smem) != cudaSuccess)
         rc = NF_EINVAL;
     const bool debug = getenv("NF_NS_DEBUG") != nullptr;
     // NF_NS_PROFILE=1: per-kernel device time of every lock-step (CUDA events, synchronous)
@@ -1541,7 +1541,7 @@ int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post,
         A(cudaMemcpyAsync(d_q, quantiles, (size_t)n_q * sizeof(double), cudaMemcpyHostToDevice, st));
         if (e == cudaSuccess && !small.empty()) {
             const size_t smem = (size_t)small_np2 * sizeof(float);
-            A(cudaFuncSetAttribute(ns_marginals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A(nf_ensure_dyn_smem((const void *)ns_marginals_kernel, smem));
             A(cudaMemcpyAsync(d_list, small.data(), small.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             if (e == cudaSuccess)
                 ns_marginals_kernel<<<(unsigned)(small.size() * d), 512, smem, st>>>(d_post, s->post_off, d_list, (int)small.size(), d,

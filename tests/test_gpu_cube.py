@@ -104,3 +104,27 @@ def test_fit_cube_dynamic_blocks(nb, tmp_path):
     _check_two_block_store(str(tmp_path / 'cube3'))
     with pytest.raises(ValueError):
         fitter.fit_cube(str(tmp_path / 'cube4'), nproc=2, devices=[0])
+
+
+def test_fit_cube_rank_concurrent_blocks(nb, tmp_path):
+    """fit_cube_rank, the SPMD form used under torchrun, with four blocks in flight from four host threads on one
+    device: blocks of different brightness (different live-set sizes, i.e. different shared-memory needs of the
+    sampler kernels) run concurrently on their own streams; every pixel is fitted exactly once, into one chunk."""
+    from nestfit_b200.synth import make_synth_stack
+    from nestfit_b200.models import ammonia
+    ut = nb.get_irdc_priors()
+    ncomp_map = np.zeros((8, 4), dtype=int)
+    ncomp_map[4:] = 1
+    noise = 0.05 + 0.25 * np.arange(8)[:, None] / 7.0 * np.ones((8, 4))      # SNR, hence nlive, differs per block
+    stack = make_synth_stack((8, 4), ut, ncomp_map=ncomp_map, n_chan=400, dv=0.158, noise=noise, seed=7)
+    fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 60}, seed=9)
+    res = fitter.fit_cube_rank(str(tmp_path / 'spmd'), 0, 1, blocks_per_gpu=4, device=0, concurrent_blocks=4)
+    assert sorted(r['block'] for r in res) == [0, 1, 2, 3]
+    store = nb.HdfStore(str(tmp_path / 'spmd'))
+    groups = list(store.iter_pix_groups())
+    assert len(groups) == 32 and all('1' in g for g in groups)
+    nbest = np.full((8, 4), -9)
+    for g in groups:
+        nbest[g.attrs['i_lon'], g.attrs['i_lat']] = g.attrs['nbest']
+    assert (nbest[:4] == 0).all() and (nbest[4:] == 1).mean() > 0.7
+    store.close()

@@ -46,3 +46,18 @@ ns = NestedSamplingBatch(blk, ut, 2, pix_ids=np.array([0, 1, 1]), nlive=40, tol=
                          method='rwalk', walks=6)
 r = ns.run(); assert np.isfinite(r['lnZ']).all(); ns.close(); blk.close()
 print("sanitize run ok")
+# [r2] products pass (packing, column sort), the ellipsoid decomposition, and a cube fit with two host threads on two
+# streams plus the background wave writer (the paths a multi-threaded caller exercises)
+from nestfit_b200.synth import make_synth_stack
+from nestfit_b200.models import ammonia
+blk = nb.PixelBlock("ammonia", xs, rng.normal(0, 0.1, (3, 2, 200)).astype(np.float32), 0.1, trans_ids=[1, 2])
+ns = NestedSamplingBatch(blk, ut, 1, nlive=[30, 40, 50], tol=1.0, n_prop=8, seed=3, max_iter=300, mmodal=True)
+r = ns.run(); p = ns.products_all(); assert p['posteriors'].shape[0] == p['row_offsets'][-1]; ns.close(); blk.close()
+stack = make_synth_stack((4, 4), ut, ncomp_map=np.ones((4, 4), dtype=int), n_chan=200, dv=0.3, noise=0.1, seed=2)
+fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 30, 'maxiter': 200}, n_prop=8,
+                       n_streams=2, pixels_per_stream=4)
+import tempfile
+with tempfile.TemporaryDirectory() as td:
+    res = fitter.fit_cube(td + '/s', nproc=1)[0]
+    assert (res['nbest'] >= 0).all()
+print("sanitize r2 ok")
