@@ -190,7 +190,7 @@ class _WaveWriter:
 
     def __init__(self, sink, store_posteriors):
         self.sink, self.store_posteriors = sink, store_posteriors
-        self.q = _queue.Queue(maxsize=2)          # at most two finished samplers keep their device pools
+        self.q = _queue.Queue(maxsize=1)          # at most one finished sampler waits with its device pool
         self.error = None
         self.seconds = 0.0
         self.rows = 0
@@ -595,14 +595,18 @@ class CubeFitter:
         self.stats['results'] = results
         return results
 
-    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None, concurrent_blocks=4):
+    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None, concurrent_blocks=None,
+                      pixels_in_flight=8192):
         """SPMD form of `fit_cube` for processes that already exist, one per GPU (torchrun): every rank calls this
         with its `rank`; blocks are claimed through the store directory (exclusive file creation), rank 0 creates
         the store and links the chunks at the end.  `barrier()` (e.g. torch.distributed.barrier) separates
-        creation, fitting and linking.  A rank keeps `concurrent_blocks` blocks in flight, each fitted by its own
-        host thread on its own CUDA stream: the blocks of an over-decomposed cube are small, and one small block
-        alone leaves the GPU underfilled (fewer runs per lock-step than the device has warps, and a thin tail per
-        wave); several in flight fill it while the claims keep the ranks balanced.
+        creation, fitting and linking.  A rank keeps `concurrent_blocks` blocks in flight (default: as many as it
+        takes to have about `pixels_in_flight` pixels on the device, at most 8), each fitted by its own host thread
+        on its own CUDA stream: the blocks of an over-decomposed cube are small, and one small block alone leaves
+        the GPU underfilled (fewer runs per lock-step than the device has warps, and a thin tail per wave).  Blocks
+        are claimed in descending order of a cost proxy (the sum over the block of the live-set sizes, which grow
+        with the peak SNR), the same order on every rank: the expensive blocks start first and the cheap ones fill
+        the end, which keeps the ranks' finishing times close.
         Returns this rank's list of per-block results."""
         self._check_partition(world, blocks_per_gpu, list(range(world)))
         barrier = barrier or (lambda: None)
@@ -619,10 +623,18 @@ class CubeFitter:
         sink = chunk_sink(store_dir, rank, self.store_posteriors)
         if self.utrans is not None and hasattr(self.utrans, 'handle'):
             self.utrans.handle(device)              # the device prior plan exists before the threads start
-        # every rank starts at its own stretch of the block list and wraps around: contiguous blocks per rank
-        # while the load is even, anything unclaimed once a rank runs out of its own
-        first = (rank * len(indices)) // world
-        order = [(first + k) % len(indices) for k in range(len(indices))]
+        # longest-processing-time-first: the same cost-sorted list on every rank, claimed from the top.  (Without a
+        # cost proxy -- a stack that cannot give the peak SNR -- every rank starts at its own stretch of the list.)
+        if hasattr(self.stack, 'block_max_snr'):
+            cost = [float(np.sum(self.mn_kwargs['nlive'] + self.nlive_snr_fact * np.nan_to_num(
+                self.stack.block_max_snr(lon, lat), nan=0.0, posinf=0.0))) for lon, lat in indices]
+            order = [int(j) for j in np.argsort(-np.asarray(cost), kind='stable')]
+        else:
+            first = (rank * len(indices)) // world
+            order = [(first + k) % len(indices) for k in range(len(indices))]
+        if concurrent_blocks is None:
+            per_block = max(1, n_pix // len(indices))
+            concurrent_blocks = int(min(8, max(1, round(pixels_in_flight / per_block))))
         results, errors, lock = [], [], threading.Lock()
         cursor = [0]
 
