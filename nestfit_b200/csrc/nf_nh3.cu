@@ -108,7 +108,8 @@ static cudaError_t nh3_upload_device_tables()
     if ((e = cudaMemcpyToSymbol(n_iem_xmax, &xmax, sizeof(double)))) return e;
     if ((e = cudaMemcpyToSymbol(n_iem_step, &step, sizeof(double)))) return e;
     if ((e = cudaMemcpyToSymbol(n_iem_inv_dx, &inv_dx, sizeof(double)))) return e;
-    return cudaSuccess;
+    // legacy-stream copies: make them visible before any kernel on a non-blocking stream can run
+    return cudaDeviceSynchronize();
 }
 
 // 1/(exp(x)-1) exactly as the reference evaluates it (table lerp inside the table

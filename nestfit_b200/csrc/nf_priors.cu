@@ -318,6 +318,8 @@ int nf_priors_create(int device, const nf_prior_desc *priors, int n_prior, const
         if (e == cudaSuccess) e = cudaMalloc(&pr->tables, sizeof(double) * n_tables);
         if (e == cudaSuccess) e = cudaMemcpy(pr->tables, tables, sizeof(double) * n_tables, cudaMemcpyHostToDevice);
     }
+    // the uploads ran in the legacy stream; their consumers run on non-blocking streams, which do not order with it
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) { nf_priors_free(pr); return (int)e; }
     *out = pr;

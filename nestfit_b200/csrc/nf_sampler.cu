@@ -1127,6 +1127,24 @@ int score(nf_sampler *s, double *params, const int32_t *pix, int64_t vpp, int64_
 template <typename T>
 cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
+// Scratch that lives for part of one call: stream-ordered allocation (NF_SYNC_ALLOC=1 falls back to cudaMalloc /
+// cudaFree, a debugging aid).
+bool ns_sync_alloc()
+{
+    static const bool on = getenv("NF_SYNC_ALLOC") != nullptr;
+    return on;
+}
+cudaError_t ns_scratch_alloc(void **p, size_t bytes, cudaStream_t st)
+{
+    return ns_sync_alloc() ? cudaMalloc(p, bytes) : cudaMallocAsync(p, bytes, st);
+}
+void ns_scratch_free(void *p, cudaStream_t st)
+{
+    if (!p) return;
+    if (ns_sync_alloc()) { cudaStreamSynchronize(st); cudaFree(p); }
+    else cudaFreeAsync(p, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1187,7 +1205,7 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     A(dalloc(&s->cand_u, CC * D)); A(dalloc(&s->cand_th, CC * D)); A(dalloc(&s->cand_l, CC));
     A(dalloc(&s->cand_pix, CC)); A(dalloc(&s->krun, R)); A(dalloc(&s->cand_off, R));
     A(dalloc(&s->bound, R * (size_t)ns_bound_stride(ndim)));
-    if (e == cudaSuccess) e = cudaMemset(s->bound, 0, R * (size_t)ns_bound_stride(ndim) * sizeof(double));
+
     A(dalloc(&s->dead_th, MS * D)); A(dalloc(&s->dead_l, MS)); A(dalloc(&s->dead_lw, MS));
     A(dalloc(&s->dead_off, R + 1)); A(dalloc(&s->dead_cap, R)); A(dalloc(&s->keep_n, R)); A(dalloc(&s->post_off, R + 1));
     A(dalloc(&s->lnZ, R)); A(dalloc(&s->H, R)); A(dalloc(&s->lmax, R)); A(dalloc(&s->lnZ_err, R));
@@ -1229,10 +1247,18 @@ int nf_ns_create(const nf_pixels *px, const nf_priors *pr, int ncomp, int model_
     if (const char *ue = getenv("NF_NS_UPDATE_EVERY")) s->update_every = atoi(ue) > 0 ? atoi(ue) : 8;
     A(cudaMallocHost((void **)&s->n_act_host, 2 * sizeof(int32_t)));
     A(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    if (e == cudaSuccess) e = cudaMemcpy(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->nlive, nlive, R * sizeof(int32_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->dead_off, s->h_dead_off->data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->dead_cap, h_cap.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice);
+    // Everything the sampler's kernels read is uploaded ON THE SAMPLER'S STREAM.  A plain cudaMemcpy from pageable
+    // memory returns once the data are staged; the DMA then runs in the legacy stream, which does not order with a
+    // non-blocking stream: under load (several samplers from several host threads) the first kernels would read
+    // pixel indices that have not arrived yet.
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(s->bound, 0, R * (size_t)ns_bound_stride(ndim) * sizeof(double), s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->pix_ids, pix_ids, R * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->nlive, nlive, R * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->dead_off, s->h_dead_off->data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->dead_cap, h_cap.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);      // the host arrays may go away after the call
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) { nf_ns_free(s); return (int)e; }
     *out = s;
@@ -1277,11 +1303,11 @@ int nf_ns_run(nf_sampler *s)
         // pixel of every (run, point): reuse cand_pix-like map built on the fly via vecs_per_pix is not
         // possible (runs index arbitrary pixels), so score run by run blocks through an explicit map
         int32_t *map = nullptr;
-        if (cudaMallocAsync((void **)&map, (size_t)n * sizeof(int32_t), st) != cudaSuccess) { rc = NF_ENOMEM; }
+        if (ns_scratch_alloc((void **)&map, (size_t)n * sizeof(int32_t), st) != cudaSuccess) { rc = NF_ENOMEM; }
         if (rc == NF_OK) {
             ns_live_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->pix_ids, map, R, NL);
             rc = score(s, s->live_th, map, NL, n, s->live_l);
-            cudaFreeAsync(map, st);
+            ns_scratch_free(map, st);
         }
         if (rc == NF_OK) {
             ns_init_state_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(s->lnZ, s->H, s->lmax, s->n_dead, s->it,
@@ -1494,7 +1520,8 @@ int nf_ns_products_rows(nf_sampler *s, int64_t *row_offsets)
         off[0] = 0;
         for (int64_t r = 0; r < R; ++r) off[(size_t)r + 1] = off[(size_t)r] + keep[(size_t)r];
         std::memcpy(row_offsets, off.data(), ((size_t)R + 1) * sizeof(int64_t));
-        e = cudaMemcpy(s->post_off, off.data(), ((size_t)R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
+        e = cudaMemcpyAsync(s->post_off, off.data(), ((size_t)R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     }
     s->launches += 1;
     if (prev >= 0) cudaSetDevice(prev);
@@ -1517,7 +1544,7 @@ int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post,
     int32_t *d_list = nullptr;
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    A(cudaMallocAsync((void **)&d_post, (size_t)(rows > 0 ? rows : 1) * w * sizeof(float), st));
+    A(ns_scratch_alloc((void **)&d_post, (size_t)(rows > 0 ? rows : 1) * w * sizeof(float), st));
     if (e == cudaSuccess) {
         ns_pack_post_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(s->dead_th, s->dead_l, s->dead_lw, s->dead_off,
                                                                             s->n_dead, s->lnZ, s->post_off, d_post, R, d);
@@ -1535,9 +1562,9 @@ int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post,
             if (n <= SMEM_ROWS) { small.push_back((int32_t)r); small_np2 = np2 > small_np2 ? np2 : small_np2; }
             else { big.push_back((int32_t)r); big_np2 = np2 > big_np2 ? np2 : big_np2; }
         }
-        A(cudaMallocAsync((void **)&d_q, (size_t)n_q * sizeof(double), st));
-        A(cudaMallocAsync((void **)&d_marg, (size_t)R * n_q * d * sizeof(double), st));
-        A(cudaMallocAsync((void **)&d_list, (size_t)R * sizeof(int32_t), st));
+        A(ns_scratch_alloc((void **)&d_q, (size_t)n_q * sizeof(double), st));
+        A(ns_scratch_alloc((void **)&d_marg, (size_t)R * n_q * d * sizeof(double), st));
+        A(ns_scratch_alloc((void **)&d_list, (size_t)R * sizeof(int32_t), st));
         A(cudaMemcpyAsync(d_q, quantiles, (size_t)n_q * sizeof(double), cudaMemcpyHostToDevice, st));
         if (e == cudaSuccess && !small.empty()) {
             const size_t smem = (size_t)small_np2 * sizeof(float);
@@ -1555,13 +1582,13 @@ int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post,
             size_t nb = (size_t)(1ull << 31) / per;
             if (nb < 1) nb = 1;
             if (nb > big.size() - b0) nb = big.size() - b0;
-            A(cudaMallocAsync((void **)&d_scratch, nb * per, st));
+            A(ns_scratch_alloc((void **)&d_scratch, nb * per, st));
             A(cudaMemcpyAsync(d_list, big.data() + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             if (e == cudaSuccess)
                 ns_marginals_kernel<<<(unsigned)(nb * d), 512, 0, st>>>(d_post, s->post_off, d_list, (int)nb, d, d_q, n_q,
                                                                        d_marg, d_scratch, big_np2);
             A(cudaStreamSynchronize(st));
-            if (d_scratch) cudaFreeAsync(d_scratch, st);
+            ns_scratch_free(d_scratch, st);
             d_scratch = nullptr;
             s->launches += 1;
             b0 += nb;
@@ -1572,10 +1599,10 @@ int nf_ns_products(nf_sampler *s, const double *quantiles, int n_q, float *post,
         A(cudaMemcpyAsync(post, d_post, (size_t)rows * w * sizeof(float), cudaMemcpyDeviceToHost, st));
     A(cudaStreamSynchronize(st));
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (d_post) cudaFreeAsync(d_post, st);
-    if (d_q) cudaFreeAsync(d_q, st);
-    if (d_marg) cudaFreeAsync(d_marg, st);
-    if (d_list) cudaFreeAsync(d_list, st);
+    ns_scratch_free(d_post, st);
+    ns_scratch_free(d_q, st);
+    ns_scratch_free(d_marg, st);
+    ns_scratch_free(d_list, st);
     cudaStreamSynchronize(st);
     if (prev >= 0) cudaSetDevice(prev);
     return (int)e;
