@@ -485,7 +485,7 @@ def _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag):
 
 
 def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, tag, blocks_per_gpu, posteriors=True,
-              concurrent_blocks=None):
+              concurrent_blocks=2):
     """One cube-fit leg through the public API: `CubeFitter.fit_cube` at N = 1, its SPMD form `fit_cube_rank` (one
     existing process per GPU, blocks claimed dynamically, one store chunk per rank) at N > 1.  The timed region
     holds everything the call does: store creation, uploads, the fit, the posterior products, the chunk writes."""
@@ -516,7 +516,8 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
     wall = time.perf_counter() - t0
     # per-rank bookkeeping -> rank 0
     mine = {"busy_s": float(fitter.stats.get("rank_fit_seconds", sum(r["seconds"] for r in results))), "n_evals": int(sum(r["n_evals"] for r in results)),
-            "n_pix": int(sum(np.asarray(r["nbest"]).size for r in results)), "blocks": len(results),
+            "n_pix": int(sum(np.asarray(r["nbest"]).size for r in results)),
+            "blocks": int(sum(len(r.get("blocks", [0])) for r in results)),
             "store_s": float(sum(r.get("store_seconds", 0.0) for r in results)),
             "store_wait_s": float(sum(r.get("store_wait_seconds", 0.0) for r in results)),
             "n_truncated": int(sum(r.get("n_truncated", 0) for r in results)), "wall_s": wall,
@@ -545,7 +546,7 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
                "nlive": "100 + 5*SNR", "tol": 1.0, "lnZ_thresh": 11, "blocks_per_gpu": blocks_per_gpu if world > 1 else 1,
                "api": "CubeFitter.fit_cube(store, nproc=1)" if world == 1 else
                       f"CubeFitter.fit_cube_rank(store, rank, {world}, blocks_per_gpu={blocks_per_gpu}, "
-                      f"concurrent_blocks={concurrent_blocks or 'auto'})",
+                      f"concurrent_blocks={concurrent_blocks})",
                "likelihood_evals_per_pixel": sum(p["n_evals"] for p in per_rank) / n_pix,
                "likelihood_evals_by_ncomp": np.sum([p["evals_by_ncomp"] for p in per_rank], axis=0).tolist(),
                "nbest_matches_truth": float((np.minimum(nbest_local, ncomp_max) == ncomp_map).mean()),
@@ -788,8 +789,8 @@ def main():
                     help="LONxLAT of the fixed configs[3]-shaped cube fitted at every N (strong scaling; 0x0 = skip)")
     ap.add_argument("--full-cube", action="store_true", help="also fit the full 512x512 configs[3] cube (default at N = 8)")
     ap.add_argument("--blocks-per-gpu", type=int, default=8, help="over-decomposition of the multi-GPU cube fit")
-    ap.add_argument("--concurrent-blocks", type=int, default=None,
-                    help="blocks a rank keeps in flight (host threads / streams; default: ~8192 pixels in flight, at most 8)")
+    ap.add_argument("--concurrent-blocks", type=int, default=2,
+                    help="groups of blocks a rank keeps in flight (host threads / streams)")
     args = ap.parse_args()
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch one process per GPU (the driver does this itself)

@@ -595,19 +595,23 @@ class CubeFitter:
         self.stats['results'] = results
         return results
 
-    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None, concurrent_blocks=None,
+    def fit_cube_rank(self, store_name, rank, world, blocks_per_gpu=8, device=0, barrier=None, concurrent_blocks=2,
                       pixels_in_flight=8192):
         """SPMD form of `fit_cube` for processes that already exist, one per GPU (torchrun): every rank calls this
         with its `rank`; blocks are claimed through the store directory (exclusive file creation), rank 0 creates
         the store and links the chunks at the end.  `barrier()` (e.g. torch.distributed.barrier) separates
-        creation, fitting and linking.  A rank keeps `concurrent_blocks` blocks in flight (default: as many as it
-        takes to have about `pixels_in_flight` pixels on the device, at most 8), each fitted by its own host thread
-        on its own CUDA stream: the blocks of an over-decomposed cube are small, and one small block alone leaves
-        the GPU underfilled (fewer runs per lock-step than the device has warps, and a thin tail per wave).  Blocks
-        are claimed in descending order of a cost proxy (the sum over the block of the live-set sizes, which grow
-        with the peak SNR), the same order on every rank: the expensive blocks start first and the cheap ones fill
-        the end, which keeps the ranks' finishing times close.
-        Returns this rank's list of per-block results."""
+        creation, fitting and linking.
+
+        The blocks of an over-decomposed cube are small, and one small block alone leaves the GPU underfilled (fewer
+        runs per lock-step than the device has warps, and a thin tail per wave).  So a rank (i) claims several
+        blocks at a time and fits them as ONE wave sequence -- as many as bring about `pixels_in_flight` pixels onto
+        the device, but never more than half of its fair share of the cube, so that the second half of the work
+        is handed out dynamically -- and (ii) keeps `concurrent_blocks` such groups in flight from as many host
+        threads, each on its own CUDA stream (the tail of one group overlaps the bulk of another, and the store
+        writer of one the sampling of the other).  Blocks are claimed in descending order of a cost proxy (the sum
+        over the block of the live-set sizes, which grow with the peak SNR), the same order on every rank: the
+        expensive blocks start first and the cheap ones fill the end, which keeps the ranks' finishing times close.
+        Returns this rank's list of per-group results (`blocks`: the block numbers of the group)."""
         self._check_partition(world, blocks_per_gpu, list(range(world)))
         barrier = barrier or (lambda: None)
         if rank == 0:
@@ -632,33 +636,39 @@ class CubeFitter:
         else:
             first = (rank * len(indices)) // world
             order = [(first + k) % len(indices) for k in range(len(indices))]
-        if concurrent_blocks is None:
-            per_block = max(1, n_pix // len(indices))
-            concurrent_blocks = int(min(8, max(1, round(pixels_in_flight / per_block))))
+        n_thr = max(1, min(int(concurrent_blocks), len(indices)))
+        per_block = max(1, n_pix // len(indices))
+        in_flight = min(float(pixels_in_flight), 0.5 * n_pix / world)
+        group = int(max(1, round(in_flight / n_thr / per_block)))
         results, errors, lock = [], [], threading.Lock()
         cursor = [0]
 
         def claim():
-            while True:
+            """Up to `group` blocks nobody has taken yet."""
+            mine = []
+            while len(mine) < group:
                 with lock:
                     if errors or cursor[0] >= len(order):
-                        return None
+                        break
                     j = order[cursor[0]]
                     cursor[0] += 1
                 try:
                     os.close(os.open(claims / f'block{j}', os.O_CREAT | os.O_EXCL | os.O_WRONLY))
-                    return j
+                    mine.append(j)
                 except FileExistsError:
                     continue
+            return mine
 
         def worker():
             while True:
-                j = claim()
-                if j is None:
+                mine = claim()
+                if not mine:
                     return
                 try:
-                    res = self.fit_block(indices[j], device=device, group_root=sink)
-                    res['block'] = j
+                    lon = np.concatenate([indices[j][0] for j in mine])
+                    lat = np.concatenate([indices[j][1] for j in mine])
+                    res = self.fit_block((lon, lat), device=device, group_root=sink)
+                    res['blocks'] = mine
                     with lock:
                         results.append(res)
                 except BaseException as exc:        # re-raised in the caller's thread
@@ -666,7 +676,6 @@ class CubeFitter:
                         errors.append(exc)
                     return
 
-        n_thr = max(1, min(int(concurrent_blocks), len(indices)))
         t0 = time.perf_counter()
         try:
             if n_thr == 1:

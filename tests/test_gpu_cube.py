@@ -119,7 +119,7 @@ def test_fit_cube_rank_concurrent_blocks(nb, tmp_path):
     stack = make_synth_stack((8, 4), ut, ncomp_map=ncomp_map, n_chan=400, dv=0.158, noise=noise, seed=7)
     fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=1, mn_kwargs={'nlive': 60}, seed=9)
     res = fitter.fit_cube_rank(str(tmp_path / 'spmd'), 0, 1, blocks_per_gpu=4, device=0, concurrent_blocks=4)
-    assert sorted(r['block'] for r in res) == [0, 1, 2, 3]
+    assert sorted(j for r in res for j in r['blocks']) == [0, 1, 2, 3]
     store = nb.HdfStore(str(tmp_path / 'spmd'))
     groups = list(store.iter_pix_groups())
     assert len(groups) == 32 and all('1' in g for g in groups)

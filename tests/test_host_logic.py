@@ -327,7 +327,7 @@ def test_fit_cube_rank_spmd_claims(tmp_path, monkeypatch, nb):
     for t in threads:
         t.join()
     assert not errs, errs
-    blocks = sorted(res['block'] for r in out for res in out[r])
+    blocks = sorted(j for r in out for res in out[r] for j in res['blocks'])
     assert blocks == list(range(12)) and all(len(out[r]) >= 1 for r in out)        # every block exactly once
     store = nb.HdfStore(str(tmp_path / 'spmd'))
     assert store.nchunks == world

@@ -47,4 +47,4 @@ else:
     with tempfile.TemporaryDirectory() as td:
         res = fitter.fit_cube_rank(td + '/s', 0, 1, blocks_per_gpu=nblk, device=0, concurrent_blocks=nthr)
 dt = time.perf_counter() - t0
-print(f"ok: {nx}x{ny} in {nblk} blocks, {nthr} in flight: {nx * ny / dt:.1f} pixels/s, {dt:.1f} s, blocks {sorted(r['block'] for r in res)}")
+print(f"ok: {nx}x{ny} in {nblk} blocks, {nthr} in flight: {nx * ny / dt:.1f} pixels/s, {dt:.1f} s, blocks {sorted(j for r in res for j in r.get('blocks', [r.get('block')]))}")
