@@ -48,6 +48,7 @@
 #define NH3_NLINES_ALL (NF_NH3_NLINES_TOTAL + NF_N2HP_NLINES_TOTAL)
 __device__ double n_line_freq[NH3_NLINES_ALL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
 __device__ float n_line_l2w[NH3_NLINES_ALL];    // log2 of the tau weights  ammonia.pyx:168-228, diazenylium.pyx:66-92
+__device__ float n_line_w[NH3_NLINES_ALL];      // the tau weights themselves
 __device__ double n_iem_y[NF_IEM_SIZE];              // 1/(exp(x_k)-1)         hyperfine.pyx:19
 __constant__ double n_iem_xmin, n_iem_xmax, n_iem_step, n_iem_inv_dx;
 
@@ -80,19 +81,22 @@ static cudaError_t nh3_upload_device_tables()
 {
     cudaError_t e = cudaSuccess;
     double freq[NH3_NLINES_ALL];
-    float l2w[NH3_NLINES_ALL];
+    float l2w[NH3_NLINES_ALL], wt[NH3_NLINES_ALL];
     for (int t = 0; t < NF_NH3_NTRANS; ++t)
         for (int i = hn_off[t]; i < hn_off[t + 1]; ++i) {
             freq[i] = (1.0 - hn_voff[i] / NF_CKMS) * hn_nu[t];
             l2w[i] = (float)std::log2(hn_wt[i]);
+            wt[i] = (float)hn_wt[i];
         }
     for (int t = 0; t < NF_N2HP_NTRANS; ++t)
         for (int i = hd_off[t]; i < hd_off[t + 1]; ++i) {
             freq[NF_NH3_NLINES_TOTAL + i] = (1.0 - hd_voff[i] / NF_CKMS) * hd_nu[t];
             l2w[NF_NH3_NLINES_TOTAL + i] = (float)std::log2(hd_wt[i]);     // -inf for a zero weight
+            wt[NF_NH3_NLINES_TOTAL + i] = (float)hd_wt[i];
         }
     if ((e = cudaMemcpyToSymbol(n_line_freq, freq, sizeof(freq)))) return e;
     if ((e = cudaMemcpyToSymbol(n_line_l2w, l2w, sizeof(l2w)))) return e;
+    if ((e = cudaMemcpyToSymbol(n_line_w, wt, sizeof(wt)))) return e;
     // hyperfine.pyx:12-20: x = linspace(XMIN, XMAX, 1000), y = 1/(exp(x)-1)
     std::vector<double> y(NF_IEM_SIZE);
     const double lo = NF_H * 23.0e9 / NF_KB, hi = NF_H * 28.0e9 / NF_KB;
@@ -145,6 +149,7 @@ struct __align__(16) Nh3Scratch {
     float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
     double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
     float tauL[32];                       // log2(log2(e) * tau_main)
+    __device__ __forceinline__ void set_tau(int i, double tau_main) { tauL[i] = log2f((float)(tau_main * NF_LOG2E)); }
 };
 
 // (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels other than J = 1, 2)
@@ -154,9 +159,8 @@ struct __align__(16) Nh3Scratch {
 // ---- S: batched set-up, lanes <-> (vector, component, spectrum) -----------------
 // MODEL 0: NH3 (voff, trot, tex, ntot, sigm, orth; ammonia.pyx:326-361);
 // MODEL 1: N2H+ (voff, tex, ltau, sigm; diazenylium.pyx:140-154).
-template <int MODEL, int NC, typename PT>
-__device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC> &sc, int64_t bb, int nb,
-                                             int lane)
+template <int MODEL, int NC, typename PT, typename SC>
+__device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, SC &sc, int64_t bb, int nb, int lane)
 {
     const int n_spec = a.n_spec;
     const int ipv = NC * n_spec;
@@ -246,7 +250,7 @@ __device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, Nh3Scratch<NC>
     const double pR1 = sm.T0_last * (aR + bR * nm1 - sm.tbg0 - sm.tbg1 * nm1);
     if (valid) {
         sc.amp[lane] = make_float4((float)pL0, (float)pR0, (float)((pL1 - pL0) / nm1), (float)((pR1 - pR0) / nm1));
-        sc.tauL[lane] = log2f((float)(tau_main * NF_LOG2E));
+        sc.set_tau(lane, tau_main);
         sc.soc[lane] = sigm / NF_CKMS;
         sc.voc[lane] = voff / NF_CKMS;
     }
@@ -385,7 +389,7 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 
     for (int64_t bb = b0 + (int64_t)warp * vpw; bb < bw_end; bb += vb) {
         const int nb = (int)min((int64_t)vb, bw_end - bb);
-        nh3_setup_batch<MODEL, NC, PT>(a, sc, bb, nb, lane);
+        nh3_setup_batch<MODEL, NC, PT, Scratch>(a, sc, bb, nb, lane);
         __syncwarp();
 
         for (int k = 0; k < nb; ++k) {
@@ -647,6 +651,389 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
     if (!data_ready) mbar_wait(bar, 0);
 }
 
+// =================================================================================================
+// Block-owner layout.  The work unit of the main loop is one (component, 8-channel block) of a spectrum: a lane owns
+// the block, walks the hyperfine lines whose windows reach it (a contiguous run of the frequency-sorted records,
+// one 32-byte record fetch per line and block) and keeps the optical depth of its eight channels in registers; the
+// radiative transfer then runs on eight channels per lane with every lane busy.  The (component, block) items of a
+// super-block (1024 channels of one spectrum) are counting-sorted by the length of their run, so that the 32 items of
+// a round have about the same number of lines.  The model of the super-block is accumulated in shared memory (items of
+// different components can own the same channels: one add per component, in turn) and the residual is taken over all
+// channels of the super-block, four per lane.
+//
+//   tp_j = -log2(e) tau_j = sum_i mA_i 2^((B_i - k2_i d) d + L_i),  d = j - R'_i (exact),  |d| <= h_i
+//   with mA_i = -log2(e) tau_main w_i kept OUTSIDE the exponent (the exponent then vanishes at the line centre,
+//   where its rounding matters most), B_i = 2 k2 phi', L_i = -k2 phi'^2.
+#define BLK_SB 128              // blocks per super-block
+#define BLK_STRIDE 132          // counting-array stride per component (slot 128 = beyond the super-block)
+
+struct __align__(16) BlkRec {
+    float mR, mk2, Bq, Lq;      // -R', -k2, B, L
+    float h, mA, pad0, pad1;    // window half width about R' (-1: no window), -log2(e) tau_main w_i
+};
+
+template <int NC>
+struct __align__(16) BlkScratch {
+    float m[BLK_SB * 8];                  // model spectrum of the current super-block (all zero between uses)
+    uint32_t items[NC * BLK_SB + 32];     // sorted items: block | component << 7 | first line << 9 | lines << 15;
+                                          // doubles as the counting array cnt[NC][BLK_STRIDE] while the list is built
+    uint32_t hist[16], base[16];          // counting sort by run length (16 classes)
+    float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
+    double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
+    float tauA[32];                       // log2(e) * tau_main
+    __device__ __forceinline__ void set_tau(int i, double tau_main) { tauA[i] = (float)(tau_main * NF_LOG2E); }
+};
+
+// tp += e * mA for a channel inside the line's window, |d| <= h
+__device__ __forceinline__ void masked_fma(float &tp, float e, float mA, float d, float h)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .f32 ad;\n"
+        "abs.f32 ad, %3;\n"
+        "setp.le.f32 p, ad, %4;\n"
+        "@p fma.rn.f32 %0, %1, %2, %0;\n"
+        "}\n"
+        : "+f"(tp)
+        : "f"(e), "f"(mA), "f"(d), "f"(h));
+}
+
+template <int MODEL, int NC, bool WRITE_PRED, typename PT>
+__global__ void __launch_bounds__(NF_THREADS, 2)
+nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *sdata = reinterpret_cast<float *>(smem_raw + 128);
+    const int data_floats = a.n_spec * a.n_pad;
+    typedef BlkScratch<NC> Scratch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nrec = a.npair;                              // records per component (lines of the widest transition)
+    const int nkey = a.nkey;                               // line keys per component (multiple of 4; 0: one super-block)
+    const size_t rec_bytes = (size_t)NC * nrec * sizeof(BlkRec), key_bytes = (size_t)NC * nkey * sizeof(short2);
+    const size_t warp_bytes = rec_bytes + key_bytes + sizeof(Scratch);
+    unsigned char *wbase = smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128 + warp * warp_bytes;
+    BlkRec *rec = reinterpret_cast<BlkRec *>(wbase);
+    short2 *keys = reinterpret_cast<short2 *>(wbase + rec_bytes);    // per line: first block, first block after its window
+    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + rec_bytes + key_bytes);
+    uint32_t *cw = sc.items;                               // cnt[c][slot] = cw[c * BLK_STRIDE + slot]
+    const uint32_t rec_addr = smem_u32(rec);
+
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    const int64_t b0 = (int64_t)blockIdx.x * tile;
+    const int64_t B = a.B_dev ? min(a.B, (int64_t)__ldg(a.B_dev)) : a.B;
+    if (b0 >= B) return;
+    constexpr bool have_data = !WRITE_PRED;
+    int64_t pix0 = 0;
+    if (have_data) {
+        pix0 = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b0) : b0 / a.vecs_per_pix;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0)
+            tma_load_1d(sdata, a.data + pix0 * a.pix_stride, (uint32_t)(data_floats * 4), bar);
+    }
+    bool data_ready = !have_data;
+    for (int idx = lane; idx < BLK_SB * 8; idx += 32) sc.m[idx] = 0.0f;
+
+    const int n_spec = a.n_spec;
+    const int ipv = NC * n_spec;
+    const int nwarps = blockDim.x >> 5;
+    const int vpw = (tile + nwarps - 1) / nwarps;
+    const int vb = min(32 / ipv, 8);
+    int64_t bw_end = b0 + (int64_t)(warp + 1) * vpw;
+    if (bw_end > b0 + tile) bw_end = b0 + tile;
+    if (bw_end > B) bw_end = B;
+    const int n_sb = (a.n_chan + BLK_SB * 8 - 1) / (BLK_SB * 8);
+
+    // FastExp's Taylor branch for 1 - exp(-tau), tau < 2^-5 (fastexp.c:265-270), in tp = -log2(e) tau
+    const float kC1 = -(float)NF_LN2, kC2 = -(float)(0.5 * NF_LN2 * NF_LN2),
+                kC3 = -(float)(NF_LN2 * NF_LN2 * NF_LN2 / 6.0);
+    const float kThr = -(float)(0.03125 * NF_LOG2E);
+
+    for (int64_t bb = b0 + (int64_t)warp * vpw; bb < bw_end; bb += vb) {
+        const int nb = (int)min((int64_t)vb, bw_end - bb);
+        nh3_setup_batch<MODEL, NC, PT, Scratch>(a, sc, bb, nb, lane);
+        __syncwarp();
+
+        for (int k = 0; k < nb; ++k) {
+            const int64_t b = bb + k;
+            int64_t pix = 0;
+            if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;
+            const bool staged = have_data && pix == pix0;
+            double lnl = 0.0;
+            for (int s = 0; s < n_spec; ++s) {
+                const NfSpecMeta &sm = a.spec[s];
+                const int NL = sm.nlines, nitems_l = NC * NL;
+                // ---- L: line records, lanes <-> (component, line) flattened; counts of super-block 0 ----
+                for (int idx = lane; idx < NC * BLK_STRIDE; idx += 32) cw[idx] = 0u;
+                __syncwarp();
+                {
+                    const double nu_min = sm.nu_min, inv_chan = sm.inv_chan;
+                    for (int t0 = 0; t0 < nitems_l; t0 += 32) {
+                        const int t = t0 + lane;
+                        const bool act = t < nitems_l;
+                        int c = 0;
+                        if (NC > 1) c += t >= NL;
+                        if (NC > 2) c += t >= 2 * NL;
+                        if (NC > 3) c += t >= 3 * NL;
+                        int i = t - c * NL;
+                        if (!act) { c = 0; i = 0; }
+                        const int it = k * ipv + c * n_spec + s;
+                        const double f = n_line_freq[sm.line_off + i];
+                        const double w = sc.soc[it] * f;                 // hyperfine.pyx:71
+                        const double nucen = f - sc.voc[it] * f;         // hyperfine.pyx:72-73
+                        const double cut = 5.0 * fabs(w);                // sqrt(12.5 / (0.5 / w^2)), hyperfine.pyx:82
+                        const double rel = nucen - nu_min;
+                        // floor((nu_cen - nu_min -/+ cut) / nu_chan), hyperfine.pyx:83-87.  cvt.rmi saturates
+                        // and maps NaN to 0, so non-finite parameters end up with an empty window.
+                        int lo = __double2int_rd((rel - cut) * inv_chan);
+                        int hi = __double2int_rd((rel + cut) * inv_chan);
+                        const bool inband = !(hi < 0 || lo > a.n_chan - 1);   // hyperfine.pyx:88
+                        const bool below = hi < 0;
+                        lo = max(lo, 0);
+                        hi = min(hi, a.n_chan - 1);
+                        const bool on = inband && hi > lo;                    // loop j in [lo, hi)
+                        // block keys, ascending in the (frequency-sorted) line index.  An in-band line with an
+                        // empty window keeps a nominal one-channel extent so that both keys stay sorted.
+                        const int hi_n = max(hi, lo + 1);
+                        const int kE = below ? -1 : (inband ? (lo >> 3) : NH3_KEY_NEVER);
+                        const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 3) + 1 : NH3_KEY_NEVER);
+                        BlkRec r;
+                        r.mR = 0.f; r.mk2 = 0.f; r.Bq = 0.f; r.Lq = 0.f; r.h = -1.0f; r.mA = 0.f; r.pad0 = 0.f; r.pad1 = 0.f;
+                        if (on) {
+                            const int r2 = lo + hi - 1;                       // twice the window midpoint
+                            const double jc = rel * inv_chan;
+                            const float phi = (float)(jc - 0.5 * (double)r2);
+                            const float sch = (float)(w * inv_chan);
+                            const float k2 = __fdividef(0.5f * (float)NF_LOG2E, sch * sch);
+                            r.mR = -0.5f * (float)r2;
+                            r.mk2 = -k2;
+                            r.Bq = 2.0f * k2 * phi;
+                            r.Lq = -k2 * phi * phi;
+                            r.h = 0.5f * (float)(hi - 1 - lo);
+                            r.mA = -(sc.tauA[it] * n_line_w[sm.line_off + i]);
+                        }
+                        if (act) {
+                            if (nkey) keys[c * nkey + i] = make_short2((short)kE, (short)kF);
+                            atomicAdd(&cw[c * BLK_STRIDE + min(max(kE, 0), BLK_SB)], 1u);
+                            atomicAdd(&cw[c * BLK_STRIDE + min(max(kF, 0), BLK_SB)], 0x100u);
+                            float4 *rp = reinterpret_cast<float4 *>(&rec[c * nrec + i]);
+                            rp[0] = make_float4(r.mR, r.mk2, r.Bq, r.Lq);
+                            rp[1] = make_float4(r.h, r.mA, 0.f, 0.f);
+                        }
+                    }
+                }
+                __syncwarp();
+
+                const char *grow = nullptr;
+                if (have_data) grow = reinterpret_cast<const char *>(a.data + pix * a.pix_stride + (int64_t)s * a.n_pad);
+                float acc = 0.0f;
+                for (int sbk = 0; sbk < n_sb; ++sbk) {
+                    const int blk0 = sbk * BLK_SB;
+                    // ---- T: items of the super-block, lanes <-> four consecutive blocks ----
+                    if (sbk > 0) {   // later super-blocks (n_chan > 1024): recount from the stored keys
+                        for (int idx = lane; idx < NC * BLK_STRIDE; idx += 32) cw[idx] = 0u;
+                        __syncwarp();
+                        for (int t0 = 0; t0 < nitems_l; t0 += 32) {
+                            const int t = t0 + lane;
+                            if (t < nitems_l) {
+                                int c = 0;
+                                if (NC > 1) c += t >= NL;
+                                if (NC > 2) c += t >= 2 * NL;
+                                if (NC > 3) c += t >= 3 * NL;
+                                const int i = t - c * NL;
+                                const short2 ky = keys[c * nkey + i];
+                                atomicAdd(&cw[c * BLK_STRIDE + min(max((int)ky.x - blk0, 0), BLK_SB)], 1u);
+                                atomicAdd(&cw[c * BLK_STRIDE + min(max((int)ky.y - blk0, 0), BLK_SB)], 0x100u);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (lane < 16) sc.hist[lane] = 0u;
+                    // inclusive prefix of {lines started, lines ended} at the lane's blocks 4 lane .. 4 lane + 3:
+                    // the lines reaching block g are the run [#ended(g), #started(g)) of the sorted records
+                    uint32_t pre[NC][4];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const uint4 q = *reinterpret_cast<const uint4 *>(&cw[c * BLK_STRIDE + 4 * lane]);
+                        const uint32_t s0 = q.x, s1 = s0 + q.y, s2 = s1 + q.z, s3 = s2 + q.w;
+                        uint32_t incl = s3;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t u = __shfl_up_sync(NF_FULL, incl, o);
+                            if (lane >= o) incl += u;
+                        }
+                        const uint32_t excl = incl - s3;
+                        pre[c][0] = excl + s0; pre[c][1] = excl + s1; pre[c][2] = excl + s2; pre[c][3] = excl + s3;
+                    }
+                    __syncwarp();     // every lane has read its counts: the item list may overwrite them
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int n = (int)(pre[c][q] & 0xffu) - (int)((pre[c][q] >> 8) & 0xffu);
+                            if (n > 0) atomicAdd(&sc.hist[15 - min(n, 15)], 1u);
+                        }
+                    __syncwarp();
+                    int nit;
+                    {
+                        const uint32_t hv = lane < 16 ? sc.hist[lane] : 0u;
+                        uint32_t incl = hv;
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1) {
+                            const uint32_t u = __shfl_up_sync(NF_FULL, incl, o);
+                            if (lane >= o) incl += u;
+                        }
+                        if (lane < 16) sc.base[lane] = incl - hv;
+                        nit = (int)__shfl_sync(NF_FULL, incl, 15);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int end = (int)(pre[c][q] & 0xffu), first = (int)((pre[c][q] >> 8) & 0xffu);
+                            const int n = end - first;
+                            if (n > 0) {
+                                const uint32_t pos = atomicAdd(&sc.base[15 - min(n, 15)], 1u);
+                                sc.items[pos] = (uint32_t)(4 * lane + q) | ((uint32_t)c << 7) | ((uint32_t)first << 9) |
+                                                ((uint32_t)n << 15);
+                            }
+                        }
+                    if (nit + lane < ((nit + 31) & ~31)) sc.items[nit + lane] = 0u;   // idle lanes of the last round
+                    __syncwarp();
+
+                    // ---- M: rounds of 32 items ----
+                    for (int r0 = 0; r0 < nit; r0 += 32) {
+                        const uint32_t item = sc.items[r0 + lane];
+                        const int n = (int)((item >> 15) & 63u), c = (int)((item >> 7) & 3u);
+                        const int blk = (int)(item & 127u), first = (int)((item >> 9) & 63u);
+                        const int T = __reduce_max_sync(NF_FULL, n);
+                        const float j0 = (float)((blk0 + blk) << 3);       // first channel of the block
+                        uint64_t x[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) x[q] = pack2(j0 + (float)(2 * q), j0 + (float)(2 * q + 1));
+                        uint32_t ra = rec_addr + (uint32_t)((c * nrec + first) * (int)sizeof(BlkRec));
+                        float tp[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) tp[q] = 0.0f;
+#pragma unroll 1
+                        for (int t = 0; t < T; ++t, ra += (uint32_t)sizeof(BlkRec)) {
+                            const float4 A = lds128(ra);
+                            const float2 H = lds64(ra + 16);
+                            const float h = t < n ? H.x : -1.0f;       // lanes whose run is shorter sit the trip out
+                            const uint64_t R2 = pack2(A.x, A.x), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z), L2 = pack2(A.w, A.w);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint64_t d2 = add2(x[q], R2);                 // exact: multiples of 1/2
+                                const uint64_t a2 = fma2(fma2(K2, d2, B2), d2, L2);
+                                float d0, d1, a0, a1;
+                                unpack2(d2, d0, d1);
+                                unpack2(a2, a0, a1);
+                                const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+                                masked_fma(tp[2 * q], e0, H.y, d0, h);
+                                masked_fma(tp[2 * q + 1], e1, H.y, d1, h);
+                            }
+                        }
+                        // radiative transfer on the lane's eight channels: 1 - exp(-tau) with FastExp's Taylor branch
+                        // below 2^-5 (fastexp.c:265-270), times the T_B amplitude (max of two lines in j)
+                        const float4 am = sc.amp[k * ipv + c * n_spec + s];        // {i_L, i_R, s_L, s_R}
+                        float val[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint64_t tp2 = pack2(tp[2 * q], tp[2 * q + 1]);
+                            float es0, es1, aL0, aL1, aR0, aR1;
+                            unpack2(mul2(tp2, fma2(tp2, fma2(tp2, pack2(kC3, kC3), pack2(kC2, kC2)), pack2(kC1, kC1))), es0, es1);
+                            const float el0 = 1.0f - ex2_approx(tp[2 * q]), el1 = 1.0f - ex2_approx(tp[2 * q + 1]);
+                            const float e0 = tp[2 * q] > kThr ? es0 : el0, e1 = tp[2 * q + 1] > kThr ? es1 : el1;
+                            unpack2(fma2(pack2(am.z, am.z), x[q], pack2(am.x, am.x)), aL0, aL1);
+                            unpack2(fma2(pack2(am.w, am.w), x[q], pack2(am.y, am.y)), aR0, aR1);
+                            val[2 * q] = fmaxf(aL0, aR0) * e0;
+                            val[2 * q + 1] = fmaxf(aL1, aR1) * e1;
+                        }
+                        // items of different components can own the same block: one component at a time
+                        float4 *mp = reinterpret_cast<float4 *>(&sc.m[blk << 3]);
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            if (c == cc && n > 0) {
+                                float4 u = mp[0], v = mp[1];
+                                u.x += val[0]; u.y += val[1]; u.z += val[2]; u.w += val[3];
+                                v.x += val[4]; v.y += val[5]; v.z += val[6]; v.w += val[7];
+                                mp[0] = u; mp[1] = v;
+                            }
+                            __syncwarp();
+                        }
+                    }
+
+                    // ---- residual over the whole super-block, four channels per lane; the model goes back to zero ----
+                    const int ch0 = blk0 << 3;
+                    const int nch = min(BLK_SB * 8, a.n_pad - ch0);      // padded channels (data and model are zero there)
+                    if (WRITE_PRED) {
+                        float *row = a.pred + (b * n_spec + s) * (int64_t)a.n_chan;
+                        const int nreal = min(BLK_SB * 8, a.n_chan - ch0);
+                        for (int j = lane; j < nreal; j += 32) row[ch0 + j] = sc.m[j];
+                        __syncwarp();
+                        for (int j = lane; j < BLK_SB * 8; j += 32) sc.m[j] = 0.0f;
+                    } else {
+                        if (!data_ready) { mbar_wait(bar, 0); data_ready = true; }
+                        for (int j4 = lane * 4; j4 < nch; j4 += 128) {
+                            float4 *mq = reinterpret_cast<float4 *>(&sc.m[j4]);
+                            const float4 mv = *mq;
+                            *mq = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 dv;
+                            if (staged) dv = *reinterpret_cast<const float4 *>(sdata + s * a.n_pad + ch0 + j4);
+                            else dv = __ldg(reinterpret_cast<const float4 *>(grow) + ((ch0 + j4) >> 2));
+                            const float r0_ = dv.x - mv.x, r1_ = dv.y - mv.y, r2_ = dv.z - mv.z, r3_ = dv.w - mv.w;
+                            acc = fmaf(r0_, r0_, acc);
+                            acc = fmaf(r1_, r1_, acc);
+                            acc = fmaf(r2_, r2_, acc);
+                            acc = fmaf(r3_, r3_, acc);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (have_data) {
+                    const double tot = warp_sum((double)acc);
+                    lnl -= tot * __ldg(a.inv2s2 + pix * n_spec + s);
+                }
+                __syncwarp();
+            }
+            if (a.lnL && lane == 0) a.lnL[b] = lnl;
+        }
+        __syncwarp();
+    }
+    // a CTA whose warps all ran out of vectors must still drain the bulk copy
+    if (!data_ready) mbar_wait(bar, 0);
+}
+
+template <int NC>
+static size_t nh3_blk_smem_bytes(const NfLikeArgs &a, int nwarps)
+{
+    const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
+    return 128 + data + ((size_t)NC * a.npair * sizeof(BlkRec) + (size_t)NC * a.nkey * sizeof(short2) +
+                         sizeof(BlkScratch<NC>)) * nwarps;
+}
+
+template <int MODEL, int NC, bool WP, typename PT>
+static cudaError_t nh3_blk_launch_one(const NfLikeArgs &a0, cudaStream_t st)
+{
+    NfLikeArgs a = a0;
+    int max_lines = 1;
+    for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
+    a.npair = max_lines;                                       // records per component
+    a.nkey = a.n_chan > BLK_SB * 8 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
+    auto kern = nf_nh3_blk_kernel<MODEL, NC, WP, PT>;
+    const size_t smem = nh3_blk_smem_bytes<NC>(a, NH3_WARPS);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = nf_ensure_dyn_smem((const void *)kern, smem);
+    if (e) return e;
+    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
+    const int64_t grid = (a.B + tile - 1) / tile;
+    if (grid <= 0) return cudaSuccess;
+    kern<<<(unsigned)grid, NF_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int NC>
 static size_t nh3_smem_bytes(const NfLikeArgs &a)
 {
@@ -675,10 +1062,21 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
+static bool nh3_use_v8()
+{
+    static const bool v8 = [] { const char *e = getenv("NF_NH3_KERNEL"); return e && e[0] == 'v'; }();
+    return v8;
+}
+
 template <int MODEL, int NC>
 static cudaError_t nh3_launch_nc(const NfLikeArgs &a, cudaStream_t st)
 {
     const bool wp = a.pred != nullptr;
+    if (!nh3_use_v8()) {
+        if (a.param_f64)
+            return wp ? nh3_blk_launch_one<MODEL, NC, true, double>(a, st) : nh3_blk_launch_one<MODEL, NC, false, double>(a, st);
+        return wp ? nh3_blk_launch_one<MODEL, NC, true, float>(a, st) : nh3_blk_launch_one<MODEL, NC, false, float>(a, st);
+    }
     if (a.param_f64)
         return wp ? nh3_launch_one<MODEL, NC, true, double>(a, st) : nh3_launch_one<MODEL, NC, false, double>(a, st);
     return wp ? nh3_launch_one<MODEL, NC, true, float>(a, st) : nh3_launch_one<MODEL, NC, false, float>(a, st);
