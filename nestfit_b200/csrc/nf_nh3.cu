@@ -654,30 +654,32 @@ nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 // =================================================================================================
 // Block-owner layout.  The work unit of the main loop is one (component, 8-channel block) of a spectrum: a lane owns
 // the block, walks the hyperfine lines whose windows reach it (a contiguous run of the frequency-sorted records,
-// one 32-byte record fetch per line and block) and keeps the optical depth of its eight channels in registers; the
+// one 24-byte record fetch per line and block) and keeps the optical depth of its eight channels in registers; the
 // radiative transfer then runs on eight channels per lane with every lane busy.  The (component, block) items of a
 // super-block (1024 channels of one spectrum) are counting-sorted by the length of their run, so that the 32 items of
-// a round have about the same number of lines.  The model of the super-block is accumulated in shared memory (items of
-// different components can own the same channels: one add per component, in turn) and the residual is taken over all
-// channels of the super-block, four per lane.
+// a round have about the same number of lines; within a class they keep the order (component, block mod 4, block / 4),
+// so the lanes of a round mostly share their line records (broadcast reads) and own blocks of ONE component.  The
+// model of the super-block is accumulated in shared memory and the residual is taken over all its channels, four per
+// lane.
 //
 //   tp_j = -log2(e) tau_j = sum_i mA_i 2^((B_i - k2_i d) d + L_i),  d = j - R'_i (exact),  |d| <= h_i
 //   with mA_i = -log2(e) tau_main w_i kept OUTSIDE the exponent (the exponent then vanishes at the line centre,
 //   where its rounding matters most), B_i = 2 k2 phi', L_i = -k2 phi'^2.
 #define BLK_SB 128              // blocks per super-block
 #define BLK_STRIDE 132          // counting-array stride per component (slot 128 = beyond the super-block)
-
-struct __align__(16) BlkRec {
-    float mR, mk2, Bq, Lq;      // -R', -k2, B, L
-    float h, mA, pad0, pad1;    // window half width about R' (-1: no window), -log2(e) tau_main w_i
-};
+#define BLK_PLANE 528           // bytes per plane of the model array: 32 float4 entries + 16 bytes of skew
+#define BLK_M_BYTES (8 * BLK_PLANE)
 
 template <int NC>
 struct __align__(16) BlkScratch {
-    float m[BLK_SB * 8];                  // model spectrum of the current super-block (all zero between uses)
+    // model spectrum of the current super-block (all zero between uses), as eight planes of float4: the half
+    // (channels 8 blk + 4 half ... + 3) of block blk lives in plane (blk & 3) * 2 + half at entry blk >> 2.  Lanes that
+    // own blocks 4 l + q (accumulation) and lanes that read channels 128 i + 4 l ... (residual) both hit 8 different
+    // 16-byte bank groups per quarter warp.
+    float m[BLK_M_BYTES / 4];
     uint32_t items[NC * BLK_SB + 32];     // sorted items: block | component << 7 | first line << 9 | lines << 15;
                                           // doubles as the counting array cnt[NC][BLK_STRIDE] while the list is built
-    uint32_t hist[16], base[16];          // counting sort by run length (16 classes)
+    uint32_t hist[16], base[16];          // counting sort by run length: class 15 - min(lines, 15)
     float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
     double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
     float tauA[32];                       // log2(e) * tau_main
@@ -698,6 +700,27 @@ __device__ __forceinline__ void masked_fma(float &tp, float e, float mA, float d
         : "f"(e), "f"(mA), "f"(d), "f"(h));
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// byte offset of the first half of block blk in the model array (second half: + BLK_PLANE)
+__device__ __forceinline__ uint32_t blk_m_off(int blk)
+{
+    return (uint32_t)((blk & 3) * (2 * BLK_PLANE) + (blk >> 2) * 16);
+}
+
+// m[block] += val, both halves
+__device__ __forceinline__ void blk_m_add(uint32_t ma, const float (&val)[8])
+{
+    float4 u = lds128(ma), v = lds128(ma + BLK_PLANE);
+    u.x += val[0]; u.y += val[1]; u.z += val[2]; u.w += val[3];
+    v.x += val[4]; v.y += val[5]; v.z += val[6]; v.w += val[7];
+    sts128(ma, u);
+    sts128(ma + BLK_PLANE, v);
+}
+
 template <int MODEL, int NC, bool WRITE_PRED, typename PT>
 __global__ void __launch_bounds__(NF_THREADS, 2)
 nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
@@ -708,16 +731,18 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
     const int data_floats = a.n_spec * a.n_pad;
     typedef BlkScratch<NC> Scratch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nrec = a.npair;                              // records per component (lines of the widest transition)
+    const int nrec = a.npair;                              // records per component (lines of the widest transition; even)
     const int nkey = a.nkey;                               // line keys per component (multiple of 4; 0: one super-block)
-    const size_t rec_bytes = (size_t)NC * nrec * sizeof(BlkRec), key_bytes = (size_t)NC * nkey * sizeof(short2);
-    const size_t warp_bytes = rec_bytes + key_bytes + sizeof(Scratch);
+    const size_t rec4_bytes = (size_t)NC * nrec * 16, rec2_bytes = (size_t)NC * nrec * 8;
+    const size_t key_bytes = (size_t)NC * nkey * sizeof(short2);
+    const size_t warp_bytes = rec4_bytes + rec2_bytes + key_bytes + sizeof(Scratch);
     unsigned char *wbase = smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128 + warp * warp_bytes;
-    BlkRec *rec = reinterpret_cast<BlkRec *>(wbase);
-    short2 *keys = reinterpret_cast<short2 *>(wbase + rec_bytes);    // per line: first block, first block after its window
-    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + rec_bytes + key_bytes);
+    float4 *rec4 = reinterpret_cast<float4 *>(wbase);                      // {-R', -k2, B, L} per (component, line)
+    float2 *rec2 = reinterpret_cast<float2 *>(wbase + rec4_bytes);        // {h, -log2(e) tau_main w}
+    short2 *keys = reinterpret_cast<short2 *>(wbase + rec4_bytes + rec2_bytes);   // first block, first block after the window
+    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + rec4_bytes + rec2_bytes + key_bytes);
     uint32_t *cw = sc.items;                               // cnt[c][slot] = cw[c * BLK_STRIDE + slot]
-    const uint32_t rec_addr = smem_u32(rec);
+    const uint32_t rec4_addr = smem_u32(rec4), rec2_addr = smem_u32(rec2), m_addr = smem_u32(sc.m);
 
     const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
     const int64_t b0 = (int64_t)blockIdx.x * tile;
@@ -733,7 +758,7 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
             tma_load_1d(sdata, a.data + pix0 * a.pix_stride, (uint32_t)(data_floats * 4), bar);
     }
     bool data_ready = !have_data;
-    for (int idx = lane; idx < BLK_SB * 8; idx += 32) sc.m[idx] = 0.0f;
+    for (int idx = lane; idx < BLK_M_BYTES / 4; idx += 32) sc.m[idx] = 0.0f;
 
     const int n_spec = a.n_spec;
     const int ipv = NC * n_spec;
@@ -744,6 +769,8 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
     if (bw_end > b0 + tile) bw_end = b0 + tile;
     if (bw_end > B) bw_end = B;
     const int n_sb = (a.n_chan + BLK_SB * 8 - 1) / (BLK_SB * 8);
+    // the lane's float4 of the model array in the residual pass: channels 128 i + 4 lane ... of the super-block
+    const uint32_t m_lane = m_addr + (uint32_t)((lane & 7) * BLK_PLANE + (lane >> 3) * 16);
 
     // FastExp's Taylor branch for 1 - exp(-tau), tau < 2^-5 (fastexp.c:265-270), in tp = -log2(e) tau
     const float kC1 = -(float)NF_LN2, kC2 = -(float)(0.5 * NF_LN2 * NF_LN2),
@@ -798,28 +825,23 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         const int hi_n = max(hi, lo + 1);
                         const int kE = below ? -1 : (inband ? (lo >> 3) : NH3_KEY_NEVER);
                         const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 3) + 1 : NH3_KEY_NEVER);
-                        BlkRec r;
-                        r.mR = 0.f; r.mk2 = 0.f; r.Bq = 0.f; r.Lq = 0.f; r.h = -1.0f; r.mA = 0.f; r.pad0 = 0.f; r.pad1 = 0.f;
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float2 r2v = make_float2(-1.0f, 0.f);
                         if (on) {
                             const int r2 = lo + hi - 1;                       // twice the window midpoint
                             const double jc = rel * inv_chan;
                             const float phi = (float)(jc - 0.5 * (double)r2);
                             const float sch = (float)(w * inv_chan);
                             const float k2 = __fdividef(0.5f * (float)NF_LOG2E, sch * sch);
-                            r.mR = -0.5f * (float)r2;
-                            r.mk2 = -k2;
-                            r.Bq = 2.0f * k2 * phi;
-                            r.Lq = -k2 * phi * phi;
-                            r.h = 0.5f * (float)(hi - 1 - lo);
-                            r.mA = -(sc.tauA[it] * n_line_w[sm.line_off + i]);
+                            r4 = make_float4(-0.5f * (float)r2, -k2, 2.0f * k2 * phi, -k2 * phi * phi);
+                            r2v = make_float2(0.5f * (float)(hi - 1 - lo), -(sc.tauA[it] * n_line_w[sm.line_off + i]));
                         }
                         if (act) {
                             if (nkey) keys[c * nkey + i] = make_short2((short)kE, (short)kF);
                             atomicAdd(&cw[c * BLK_STRIDE + min(max(kE, 0), BLK_SB)], 1u);
                             atomicAdd(&cw[c * BLK_STRIDE + min(max(kF, 0), BLK_SB)], 0x100u);
-                            float4 *rp = reinterpret_cast<float4 *>(&rec[c * nrec + i]);
-                            rp[0] = make_float4(r.mR, r.mk2, r.Bq, r.Lq);
-                            rp[1] = make_float4(r.h, r.mA, 0.f, 0.f);
+                            rec4[c * nrec + i] = r4;
+                            rec2[c * nrec + i] = r2v;
                         }
                     }
                 }
@@ -827,7 +849,7 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
 
                 const char *grow = nullptr;
                 if (have_data) grow = reinterpret_cast<const char *>(a.data + pix * a.pix_stride + (int64_t)s * a.n_pad);
-                float acc = 0.0f;
+                uint64_t acc_a = 0ull, acc_b = 0ull;        // packed FP32x2 sums of squared residuals
                 for (int sbk = 0; sbk < n_sb; ++sbk) {
                     const int blk0 = sbk * BLK_SB;
                     // ---- T: items of the super-block, lanes <-> four consecutive blocks ----
@@ -867,6 +889,7 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         pre[c][0] = excl + s0; pre[c][1] = excl + s1; pre[c][2] = excl + s2; pre[c][3] = excl + s3;
                     }
                     __syncwarp();     // every lane has read its counts: the item list may overwrite them
+                    // class sizes (the hardware aggregates the lanes that add to one class)
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
@@ -888,6 +911,8 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         nit = (int)__shfl_sync(NF_FULL, incl, 15);
                     }
                     __syncwarp();
+                    // placement: classes in descending run length; within a class the candidate slots follow one
+                    // another in the order (component, block mod 4)
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
@@ -913,14 +938,15 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         uint64_t x[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) x[q] = pack2(j0 + (float)(2 * q), j0 + (float)(2 * q + 1));
-                        uint32_t ra = rec_addr + (uint32_t)((c * nrec + first) * (int)sizeof(BlkRec));
+                        const int ri = c * nrec + first;
+                        uint32_t ra4 = rec4_addr + (uint32_t)(ri * 16), ra2 = rec2_addr + (uint32_t)(ri * 8);
                         float tp[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) tp[q] = 0.0f;
 #pragma unroll 1
-                        for (int t = 0; t < T; ++t, ra += (uint32_t)sizeof(BlkRec)) {
-                            const float4 A = lds128(ra);
-                            const float2 H = lds64(ra + 16);
+                        for (int t = 0; t < T; ++t, ra4 += 16u, ra2 += 8u) {
+                            const float4 A = lds128(ra4);
+                            const float2 H = lds64(ra2);
                             const float h = t < n ? H.x : -1.0f;       // lanes whose run is shorter sit the trip out
                             const uint64_t R2 = pack2(A.x, A.x), K2 = pack2(A.y, A.y), B2 = pack2(A.z, A.z), L2 = pack2(A.w, A.w);
 #pragma unroll
@@ -951,17 +977,19 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                             val[2 * q] = fmaxf(aL0, aR0) * e0;
                             val[2 * q + 1] = fmaxf(aL1, aR1) * e1;
                         }
-                        // items of different components can own the same block: one component at a time
-                        float4 *mp = reinterpret_cast<float4 *>(&sc.m[blk << 3]);
-#pragma unroll
-                        for (int cc = 0; cc < NC; ++cc) {
-                            if (c == cc && n > 0) {
-                                float4 u = mp[0], v = mp[1];
-                                u.x += val[0]; u.y += val[1]; u.z += val[2]; u.w += val[3];
-                                v.x += val[4]; v.y += val[5]; v.z += val[6]; v.w += val[7];
-                                mp[0] = u; mp[1] = v;
-                            }
+                        // accumulate into the model.  Items of ONE component own different blocks (the usual round);
+                        // a round that holds several components adds them in turn
+                        const uint32_t ma = m_addr + blk_m_off(blk);
+                        const int c_first = __shfl_sync(NF_FULL, c, 0);
+                        if (__all_sync(NF_FULL, n == 0 || c == c_first)) {
+                            if (n > 0) blk_m_add(ma, val);
                             __syncwarp();
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < NC; ++cc) {
+                                if (c == cc && n > 0) blk_m_add(ma, val);
+                                __syncwarp();
+                            }
                         }
                     }
 
@@ -971,29 +999,49 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                     if (WRITE_PRED) {
                         float *row = a.pred + (b * n_spec + s) * (int64_t)a.n_chan;
                         const int nreal = min(BLK_SB * 8, a.n_chan - ch0);
-                        for (int j = lane; j < nreal; j += 32) row[ch0 + j] = sc.m[j];
+                        for (int j = lane; j < nreal; j += 32) {
+                            const int bq = j >> 3;
+                            row[ch0 + j] = sc.m[(blk_m_off(bq) + ((j >> 2) & 1) * BLK_PLANE) / 4 + (j & 3)];
+                        }
                         __syncwarp();
-                        for (int j = lane; j < BLK_SB * 8; j += 32) sc.m[j] = 0.0f;
+                        for (int idx = lane; idx < BLK_M_BYTES / 4; idx += 32) sc.m[idx] = 0.0f;
                     } else {
                         if (!data_ready) { mbar_wait(bar, 0); data_ready = true; }
-                        for (int j4 = lane * 4; j4 < nch; j4 += 128) {
-                            float4 *mq = reinterpret_cast<float4 *>(&sc.m[j4]);
-                            const float4 mv = *mq;
-                            *mq = make_float4(0.f, 0.f, 0.f, 0.f);
-                            float4 dv;
-                            if (staged) dv = *reinterpret_cast<const float4 *>(sdata + s * a.n_pad + ch0 + j4);
-                            else dv = __ldg(reinterpret_cast<const float4 *>(grow) + ((ch0 + j4) >> 2));
-                            const float r0_ = dv.x - mv.x, r1_ = dv.y - mv.y, r2_ = dv.z - mv.z, r3_ = dv.w - mv.w;
-                            acc = fmaf(r0_, r0_, acc);
-                            acc = fmaf(r1_, r1_, acc);
-                            acc = fmaf(r2_, r2_, acc);
-                            acc = fmaf(r3_, r3_, acc);
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const uint64_t neg1 = pack2(-1.0f, -1.0f);
+                        if (staged) {
+                            const uint32_t dl = smem_u32(sdata + s * a.n_pad + ch0) + (uint32_t)lane * 16u;
+#pragma unroll 4
+                            for (int j4 = lane * 4, i = 0; j4 < nch; j4 += 128, ++i) {
+                                const float4 mv = lds128(m_lane + (uint32_t)i * 64u);
+                                const float4 dv = lds128(dl + (uint32_t)i * 512u);
+                                sts128(m_lane + (uint32_t)i * 64u, zero4);
+                                const uint64_t ra_ = fma2(pack2(mv.x, mv.y), neg1, pack2(dv.x, dv.y));
+                                const uint64_t rb_ = fma2(pack2(mv.z, mv.w), neg1, pack2(dv.z, dv.w));
+                                acc_a = fma2(ra_, ra_, acc_a);
+                                acc_b = fma2(rb_, rb_, acc_b);
+                            }
+                        } else {
+                            const float4 *dg = reinterpret_cast<const float4 *>(grow) + (ch0 >> 2) + lane;
+#pragma unroll 4
+                            for (int j4 = lane * 4, i = 0; j4 < nch; j4 += 128, ++i) {
+                                const float4 mv = lds128(m_lane + (uint32_t)i * 64u);
+                                const float4 dv = __ldg(dg + i * 32);
+                                sts128(m_lane + (uint32_t)i * 64u, zero4);
+                                const uint64_t ra_ = fma2(pack2(mv.x, mv.y), neg1, pack2(dv.x, dv.y));
+                                const uint64_t rb_ = fma2(pack2(mv.z, mv.w), neg1, pack2(dv.z, dv.w));
+                                acc_a = fma2(ra_, ra_, acc_a);
+                                acc_b = fma2(rb_, rb_, acc_b);
+                            }
                         }
                     }
                     __syncwarp();
                 }
                 if (have_data) {
-                    const double tot = warp_sum((double)acc);
+                    float a0, a1, a2, a3;
+                    unpack2(acc_a, a0, a1);
+                    unpack2(acc_b, a2, a3);
+                    const double tot = warp_sum((double)((a0 + a1) + (a2 + a3)));
                     lnl -= tot * __ldg(a.inv2s2 + pix * n_spec + s);
                 }
                 __syncwarp();
@@ -1010,8 +1058,7 @@ template <int NC>
 static size_t nh3_blk_smem_bytes(const NfLikeArgs &a, int nwarps)
 {
     const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
-    return 128 + data + ((size_t)NC * a.npair * sizeof(BlkRec) + (size_t)NC * a.nkey * sizeof(short2) +
-                         sizeof(BlkScratch<NC>)) * nwarps;
+    return 128 + data + ((size_t)NC * a.npair * 24 + (size_t)NC * a.nkey * sizeof(short2) + sizeof(BlkScratch<NC>)) * nwarps;
 }
 
 template <int MODEL, int NC, bool WP, typename PT>
@@ -1020,7 +1067,7 @@ static cudaError_t nh3_blk_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     NfLikeArgs a = a0;
     int max_lines = 1;
     for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
-    a.npair = max_lines;                                       // records per component
+    a.npair = (max_lines + 1) & ~1;                            // records per component (even: 16-byte aligned arrays)
     a.nkey = a.n_chan > BLK_SB * 8 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
     auto kern = nf_nh3_blk_kernel<MODEL, NC, WP, PT>;
     const size_t smem = nh3_blk_smem_bytes<NC>(a, NH3_WARPS);
