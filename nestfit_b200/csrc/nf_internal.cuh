@@ -75,7 +75,7 @@ struct nf_priors {
 struct NfLikeArgs {
     const float *data;          // may be NULL (predict only)
     const double *inv2s2;
-    const float *d2chunk;       // per pixel, spectrum and 32-channel chunk: sum of d^2 (chunks no line touches)
+    const float *d2chunk;       // per pixel, spectrum and 32-channel chunk: sum of d^2 (Gaussian-model kernel)
     const void *params;
     const int32_t *pix_of_vec;  // may be NULL
     int64_t vecs_per_pix;
@@ -88,7 +88,8 @@ struct NfLikeArgs {
     int ncomp, n_spec, n_chan, n_pad;
     int cold, lte;
     int tile_vecs;              // parameter vectors per CTA tile (0 -> NF_TILE_VECS)
-    int npair;                  // hyperfine kernel: pair records per parity (set by the launcher)
+    int npair;                  // hyperfine kernel: line records per component (set by the launcher)
+    int stage;                  // hyperfine kernel: the tile's pixel is staged in shared memory (set by the launcher)
     int nkey;                   // hyperfine kernel: line keys per component (set by the launcher)
     NfSpecMeta spec[NF_MAX_SPEC];
 };

@@ -1,33 +1,33 @@
 // Fused hyperfine synthesis + radiative transfer + chi-square kernel (sm_100a) for the NH3
 // (J,K) inversion lines and N2H+ J = 1-0, 2-1, 3-2.
 //
-// One warp scores one parameter vector against one pixel.  In the FP32 main loop lanes <->
-// channels on 64-channel chunks: lane l owns channels 64 g + l and 64 g + l + 32, so every pair
-// record fetched from shared memory serves four windowed Gaussians per lane.  Everything around
-// the main loop is laid out so that lanes are busy:
+// One warp scores one parameter vector against one pixel, in four phases:
 //   S  set-up, batched over the warp's next few vectors: lanes <-> (vector, component,
 //      spectrum); partition function, main-line optical depth and the brightness
 //      amplitude in FP64                                   (ammonia.pyx:289-361,
 //                                                           diazenylium.pyx:140-154)
 //   L  per (vector, spectrum): lanes <-> (component, hyperfine line), flattened; window
-//      [lo, hi) with the reference's floor rule in FP64    (hyperfine.pyx:68-96)
-//   T  work list of a super-block: lanes <-> chunks; the lines touching a chunk are a
-//      contiguous run of the frequency-sorted records (counting + warp scan); the non-empty
-//      (chunk, component) runs are compacted into a flat list
-//   M  main loop over that list: two lines x two channels per trip in packed FP32x2
-//      (FADD2/FFMA2), MUFU.EX2, one compare per term (windows are stored symmetric about
-//      their own midpoint), then the radiative transfer and, on the last component of a
-//      chunk, the residual                                 (hyperfine.pyx:98-113,
-//                                                           core.pyx:522-530)
-//   Chunks no line touches are never visited: their sum of d^2 comes from a per-pixel table.
+//      [lo, hi) with the reference's floor rule in FP64, one 24-byte record per line
+//                                                          (hyperfine.pyx:68-96)
+//   T  item list of a super-block (1024 channels of one spectrum): lanes <-> four consecutive
+//      8-channel blocks; the lines reaching a block are a contiguous run of the frequency-
+//      sorted records (counting + warp scan); the non-empty (component, block) items are
+//      counting-sorted by the length of their run
+//   M  rounds of 32 items: a lane owns ONE 8-channel block of ONE component, walks its run
+//      of lines (one record fetch per line, eight windowed Gaussians in packed FP32x2
+//      FADD2/FFMA2 + MUFU.EX2, one compare per term) with the optical depth of its eight
+//      channels in registers, applies the radiative transfer to them and adds the result
+//      to the model of the super-block in shared memory; then the residual of the whole
+//      super-block, four channels per lane             (hyperfine.pyx:98-113, core.pyx:522-530)
 //
 // Arithmetic identities used (all exact up to FP32 rounding):
 //   tau_j = sum_i tau_main w_i exp(-k_i (j - c_i)^2) is accumulated as
-//   tp_j = -log2(e) tau_j = -sum_i 2^(L_i + (B_i - k2_i d) d),  d = j - R'_i (exact),
-//   with log2(log2(e) tau_main w_i) folded into L_i, so exp(-tau_j) = 2^tp_j.
+//   tp_j = -log2(e) tau_j = sum_i mA_i 2^((B_i - k2_i d) d + L_i),  d = j - R'_i (exact),
+//   with R' the midpoint of the line's window (so the window test is |d| <= h), B = 2 k2 phi',
+//   L = -k2 phi'^2 and mA_i = -log2(e) tau_main w_i kept OUTSIDE the exponent: the exponent
+//   vanishes at the line centre, where its rounding matters most.  exp(-tau_j) = 2^tp_j.
 //   FastExp semantics (nestfit/core/fastexp.c:234-283): exp(-x) of the float-rounded
 //   argument -> MUFU.EX2; Taylor-3 branch below 2^-5 kept for 1 - exp(-tau).
-//   A negative main-line optical depth (outside every prior) gives NaN, not the reference's sign.
 
 #include <cmath>
 #include <cstdio>
@@ -47,8 +47,7 @@
 // NH3 lines first, then the N2H+ lines (NfSpecMeta::line_off indexes this flat list)
 #define NH3_NLINES_ALL (NF_NH3_NLINES_TOTAL + NF_N2HP_NLINES_TOTAL)
 __device__ double n_line_freq[NH3_NLINES_ALL];  // (1 - voff_i/c) * nu0   hyperfine.pyx:70
-__device__ float n_line_l2w[NH3_NLINES_ALL];    // log2 of the tau weights  ammonia.pyx:168-228, diazenylium.pyx:66-92
-__device__ float n_line_w[NH3_NLINES_ALL];      // the tau weights themselves
+__device__ float n_line_w[NH3_NLINES_ALL];      // the tau weights  ammonia.pyx:168-228, diazenylium.pyx:66-92
 __device__ double n_iem_y[NF_IEM_SIZE];              // 1/(exp(x_k)-1)         hyperfine.pyx:19
 __constant__ double n_iem_xmin, n_iem_xmax, n_iem_step, n_iem_inv_dx;
 
@@ -81,21 +80,18 @@ static cudaError_t nh3_upload_device_tables()
 {
     cudaError_t e = cudaSuccess;
     double freq[NH3_NLINES_ALL];
-    float l2w[NH3_NLINES_ALL], wt[NH3_NLINES_ALL];
+    float wt[NH3_NLINES_ALL];
     for (int t = 0; t < NF_NH3_NTRANS; ++t)
         for (int i = hn_off[t]; i < hn_off[t + 1]; ++i) {
             freq[i] = (1.0 - hn_voff[i] / NF_CKMS) * hn_nu[t];
-            l2w[i] = (float)std::log2(hn_wt[i]);
             wt[i] = (float)hn_wt[i];
         }
     for (int t = 0; t < NF_N2HP_NTRANS; ++t)
         for (int i = hd_off[t]; i < hd_off[t + 1]; ++i) {
             freq[NF_NH3_NLINES_TOTAL + i] = (1.0 - hd_voff[i] / NF_CKMS) * hd_nu[t];
-            l2w[NF_NH3_NLINES_TOTAL + i] = (float)std::log2(hd_wt[i]);     // -inf for a zero weight
             wt[NF_NH3_NLINES_TOTAL + i] = (float)hd_wt[i];
         }
     if ((e = cudaMemcpyToSymbol(n_line_freq, freq, sizeof(freq)))) return e;
-    if ((e = cudaMemcpyToSymbol(n_line_l2w, l2w, sizeof(l2w)))) return e;
     if ((e = cudaMemcpyToSymbol(n_line_w, wt, sizeof(wt)))) return e;
     // hyperfine.pyx:12-20: x = linspace(XMIN, XMAX, 1000), y = 1/(exp(x)-1)
     std::vector<double> y(NF_IEM_SIZE);
@@ -129,28 +125,6 @@ __device__ double nh3_iemtex(double x)
     }
     return 1.0 / expm1(x);
 }
-
-// Two adjacent hyperfine lines of one (component, spectrum), element-interleaved for the
-// packed FP32x2 pipeline: 48 bytes = two LDS.128 + one LDS.64.
-struct __align__(16) Nh3Pair {
-    float4 a;   // {-R'_0, -R'_1, -k2_0, -k2_1}     R' = window midpoint (multiple of 1/2)
-    float4 b;   // {B_0, B_1, L_0, L_1}             B = 2 k2 phi', L = log2(log2e tau w) - k2 phi'^2
-    float4 h;   // {h_0, h_1, -, -}                 window <=> |j - R'| <= h
-};
-
-// Per-warp scratch: the pair records and the line keys (capacities set at launch from the
-// transitions in use) followed by this fixed part.
-template <int NC>
-struct __align__(16) Nh3Scratch {
-    uint4 seg[32 * NC];                   // work list of a super-block, one record per (chunk, component) that has
-                                          // lines: {first pair smem address | pairs << 18, amplitude smem address,
-                                          // data byte offset of the chunk | last-of-chunk << 31, float(32 chunk)};
-                                          // doubles as the counting array cnt[NC][36] while the list is built
-    float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
-    double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
-    float tauL[32];                       // log2(log2(e) * tau_main)
-    __device__ __forceinline__ void set_tau(int i, double tau_main) { tauL[i] = log2f((float)(tau_main * NF_LOG2E)); }
-};
 
 // (2J+1) * h (B J(J+1) + (C-B) J^2) / k_B in kelvin, FP32 (levels other than J = 1, 2)
 #define NH3_BK_F ((float)(NF_HK * NF_BROT))
@@ -256,30 +230,10 @@ __device__ __noinline__ void nh3_setup_batch(const NfLikeArgs &a, SC &sc, int64_
     }
 }
 
-// tp -= e for lanes whose channel lies inside the line's window, |d| <= h
-__device__ __forceinline__ void masked_sub(float &tp, float e, float d, float h)
-{
-    asm("{\n"
-        ".reg .pred p;\n"
-        ".reg .f32 ad;\n"
-        "abs.f32 ad, %2;\n"
-        "setp.le.f32 p, ad, %3;\n"
-        "@p sub.f32 %0, %0, %1;\n"
-        "}\n"
-        : "+f"(tp)
-        : "f"(e), "f"(d), "f"(h));
-}
-
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ float2 lds64(uint32_t addr)
@@ -289,382 +243,18 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
     return v;
 }
 
-// Two hyperfine lines at one channel x (packed twice): the run touches only one half of the chunk.
-__device__ __forceinline__ void nh3_pair_term1(float &tp, uint32_t ra, uint64_t x2)
-{
-    const float4 A = lds128(ra), B = lds128(ra + 16);
-    const float2 H = lds64(ra + 32);
-    const uint64_t d2 = add2(x2, pack2(A.x, A.y));                         // exact: multiples of 1/2
-    const uint64_t t2 = fma2(pack2(A.z, A.w), d2, pack2(B.x, B.y));
-    const uint64_t a2 = fma2(t2, d2, pack2(B.z, B.w));
-    float d0, d1, a0, a1;
-    unpack2(d2, d0, d1);
-    unpack2(a2, a0, a1);
-    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-    masked_sub(tp, e0, d0, H.x);
-    masked_sub(tp, e1, d1, H.y);
-}
-
-// Two hyperfine lines (2q+p and 2q+p+1) at the lane's two channels xa and xb = xa + 32 (each packed
-// twice): one record fetch, four windowed Gaussian terms.
-__device__ __forceinline__ void nh3_pair_term(float &tpa, float &tpb, uint32_t ra, uint64_t xa2, uint64_t xb2)
-{
-    const float4 A = lds128(ra), B = lds128(ra + 16);
-    const float2 H = lds64(ra + 32);
-    const uint64_t R2 = pack2(A.x, A.y), K2 = pack2(A.z, A.w), B2 = pack2(B.x, B.y), L2 = pack2(B.z, B.w);
-    const uint64_t da2 = add2(xa2, R2), db2 = add2(xb2, R2);              // exact: multiples of 1/2
-    const uint64_t ta2 = fma2(K2, da2, B2), tb2 = fma2(K2, db2, B2);
-    const uint64_t aa2 = fma2(ta2, da2, L2), ab2 = fma2(tb2, db2, L2);
-    float da0, da1, db0, db1, aa0, aa1, ab0, ab1;
-    unpack2(da2, da0, da1);
-    unpack2(db2, db0, db1);
-    unpack2(aa2, aa0, aa1);
-    unpack2(ab2, ab0, ab1);
-    const float ea0 = ex2_approx(aa0), ea1 = ex2_approx(aa1), eb0 = ex2_approx(ab0), eb1 = ex2_approx(ab1);
-    masked_sub(tpa, ea0, da0, H.x);
-    masked_sub(tpa, ea1, da1, H.y);
-    masked_sub(tpb, eb0, db0, H.x);
-    masked_sub(tpb, eb1, db1, H.y);
-}
-
 // ---- the fused kernel ---------------------------------------------------------
-// WRITE_PRED = false: log-likelihood against the pixel's data (a.data, a.lnL);
-// WRITE_PRED = true : model spectra only (a.pred), no data are read.
-template <int MODEL, int NC, bool WRITE_PRED, typename PT>
-__global__ void __launch_bounds__(NF_THREADS, (NC <= 3 ? 4 : 3))
-nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    float *sdata = reinterpret_cast<float *>(smem_raw + 128);
-    const int data_floats = a.n_spec * a.n_pad;
-    typedef Nh3Scratch<NC> Scratch;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // pair[c][p][q] holds lines (2q+p, 2q+p+1); npair pairs per parity
-    const int npair = a.npair;
-    const int nkey = a.nkey;                               // line keys per component (multiple of 4)
-    const size_t pair_bytes = (size_t)NC * 2 * npair * sizeof(Nh3Pair), key_bytes = (size_t)NC * nkey * sizeof(short2);
-    const size_t warp_bytes = pair_bytes + key_bytes + sizeof(Scratch);
-    unsigned char *wbase = smem_raw + 128 + (((size_t)data_floats * 4 + 127) / 128) * 128 + warp * warp_bytes;
-    float *pairf = reinterpret_cast<float *>(wbase);
-    short2 *keys = reinterpret_cast<short2 *>(wbase + pair_bytes);   // per line: first chunk, first chunk after its window
-    Scratch &sc = *reinterpret_cast<Scratch *>(wbase + pair_bytes + key_bytes);
-    uint32_t *cw = reinterpret_cast<uint32_t *>(sc.seg);   // cnt[c][g] = cw[c * 36 + g]
-    const uint32_t pair_addr = smem_u32(pairf);
-
-    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
-    const int64_t b0 = (int64_t)blockIdx.x * tile;
-    // the vector count may live on the device (lock-step sampler): a.B then only sized the grid
-    const int64_t B = a.B_dev ? min(a.B, (int64_t)__ldg(a.B_dev)) : a.B;
-    if (b0 >= B) return;
-    constexpr bool have_data = !WRITE_PRED;
-    int64_t pix0 = 0;
-    if (have_data) {
-        pix0 = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b0) : b0 / a.vecs_per_pix;
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        if (tid == 0)
-            tma_load_1d(sdata, a.data + pix0 * a.pix_stride, (uint32_t)(data_floats * 4), bar);
-    }
-    bool data_ready = !have_data;
-
-    const int n_spec = a.n_spec;
-    const int ipv = NC * n_spec;
-    const int nchunks = (a.n_chan + 63) >> 6;        // 64-channel chunks (rows are padded to a multiple of 64)
-    float lane_f;                 // kept in registers (volatile asm: never rematerialised inside the main loop)
-    uint32_t lane4;
-    asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(lane_f) : "r"(lane));
-    asm volatile("shl.b32 %0, %1, 2;" : "=r"(lane4) : "r"(lane));
-    // the warp's vectors: a contiguous slice of the tile, set up in batches of vb
-    const int vpw = (tile + NH3_WARPS - 1) / NH3_WARPS;
-    const int vb = min(32 / ipv, 8);
-    int64_t bw_end = b0 + (int64_t)(warp + 1) * vpw;
-    if (bw_end > b0 + tile) bw_end = b0 + tile;
-    if (bw_end > B) bw_end = B;
-
-    // FastExp's Taylor branch for 1 - exp(-tau), tau < 2^-5 (fastexp.c:265-270), in tp = -log2(e) tau
-    const float kC1 = -(float)NF_LN2, kC2 = -(float)(0.5 * NF_LN2 * NF_LN2),
-                kC3 = -(float)(NF_LN2 * NF_LN2 * NF_LN2 / 6.0);
-    const float kThr = -(float)(0.03125 * NF_LOG2E);
-
-    for (int64_t bb = b0 + (int64_t)warp * vpw; bb < bw_end; bb += vb) {
-        const int nb = (int)min((int64_t)vb, bw_end - bb);
-        nh3_setup_batch<MODEL, NC, PT, Scratch>(a, sc, bb, nb, lane);
-        __syncwarp();
-
-        for (int k = 0; k < nb; ++k) {
-            const int64_t b = bb + k;
-            int64_t pix = 0;
-            if (have_data) pix = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b) : b / a.vecs_per_pix;
-            double lnl = 0.0;
-            for (int s = 0; s < n_spec; ++s) {
-                const NfSpecMeta &sm = a.spec[s];
-                // ---- L: line records, lanes <-> (component, line) flattened ----
-                for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
-                __syncwarp();
-                {
-                    const int NL = sm.nlines, nitems = NC * NL;
-                    const double nu_min = sm.nu_min, inv_chan = sm.inv_chan;
-                    for (int t0 = 0; t0 < nitems; t0 += 32) {
-                        const int t = t0 + lane;
-                        const bool act = t < nitems;
-                        int c = 0;
-                        if (NC > 1) c += t >= NL;
-                        if (NC > 2) c += t >= 2 * NL;
-                        if (NC > 3) c += t >= 3 * NL;
-                        int i = t - c * NL;
-                        if (!act) { c = 0; i = 0; }
-                        const int it = k * ipv + c * n_spec + s;
-                        const double f = n_line_freq[sm.line_off + i];
-                        const double w = sc.soc[it] * f;                 // hyperfine.pyx:71
-                        const double nucen = f - sc.voc[it] * f;         // hyperfine.pyx:72-73
-                        const double cut = 5.0 * fabs(w);                // sqrt(12.5 / (0.5 / w^2)), hyperfine.pyx:82
-                        const double rel = nucen - nu_min;
-                        // floor((nu_cen - nu_min -/+ cut) / nu_chan), hyperfine.pyx:83-87.  cvt.rmi saturates
-                        // and maps NaN to 0, so non-finite parameters end up with an empty window.
-                        int lo = __double2int_rd((rel - cut) * inv_chan);
-                        int hi = __double2int_rd((rel + cut) * inv_chan);
-                        const bool inband = !(hi < 0 || lo > a.n_chan - 1);   // hyperfine.pyx:88
-                        const bool below = hi < 0;
-                        lo = max(lo, 0);
-                        hi = min(hi, a.n_chan - 1);
-                        const bool on = inband && hi > lo;                    // loop j in [lo, hi)
-                        // chunk keys, ascending in the (frequency-sorted) line index.  An in-band line with an
-                        // empty window keeps a nominal one-channel extent so that both keys stay sorted.
-                        const int hi_n = max(hi, lo + 1);
-                        const int kE = below ? -1 : (inband ? (lo >> 6) : NH3_KEY_NEVER);
-                        const int kF = below ? -1 : (inband ? ((hi_n - 1) >> 6) + 1 : NH3_KEY_NEVER);
-                        float mR = 0.f, mk2 = 0.f, Bq = 0.f, Lq = -INFINITY, hh = -1.0f;
-                        if (on) {
-                            const int r2 = lo + hi - 1;                       // twice the window midpoint
-                            const double jc = rel * inv_chan;
-                            const float phi = (float)(jc - 0.5 * (double)r2);
-                            const float sch = (float)(w * inv_chan);
-                            const float k2 = __fdividef(0.5f * (float)NF_LOG2E, sch * sch);
-                            mR = -0.5f * (float)r2;
-                            mk2 = -k2;
-                            Bq = 2.0f * k2 * phi;
-                            Lq = sc.tauL[it] + n_line_l2w[sm.line_off + i] - k2 * phi * phi;
-                            hh = 0.5f * (float)(hi - 1 - lo);
-                        }
-                        if (act) {
-                            if (nkey) keys[c * nkey + i] = make_short2((short)kE, (short)kF);
-                            // counts of super-block 0, four 8-bit fields per (component, chunk): lines starting
-                            // here, lines ended before here, lines starting here in the chunk's first half,
-                            // lines whose last channel lies in the second half of the chunk before this one
-                            const uint32_t tA = (inband && (lo & 63) < 32) ? 0x10000u : 0u;
-                            const uint32_t tB = (inband && ((hi_n - 1) & 63) >= 32) ? 0x1000000u : 0u;
-                            atomicAdd(&cw[c * 36 + min(max(kE, 0), 32)], 1u + tA);
-                            atomicAdd(&cw[c * 36 + min(max(kF, 0), 32)], 0x100u + tB);
-                            // line i is element 0 of pair (p = i & 1, q = i >> 1) and element 1 of the pair
-                            // of the other parity that starts one line earlier
-                            float *pb = pairf + c * (2 * npair * 12);
-                            float *e0 = pb + ((i & 1) * npair + (i >> 1)) * 12;
-                            e0[0] = mR; e0[2] = mk2; e0[4] = Bq; e0[6] = Lq; e0[8] = hh;
-                            if (i > 0) {
-                                float *e1 = pb + (((i - 1) & 1) * npair + ((i - 1) >> 1)) * 12;
-                                e1[1] = mR; e1[3] = mk2; e1[5] = Bq; e1[7] = Lq; e1[9] = hh;
-                            }
-                            if (i == NL - 1) {   // the null line NL closes an odd run that ends at the last line
-                                e0[1] = 0.f; e0[3] = 0.f; e0[5] = 0.f; e0[7] = -INFINITY; e0[9] = -1.0f;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (!data_ready) { mbar_wait(bar, 0); data_ready = true; }
-
-                // amplitude lines of this spectrum: one float4 {intercept_L, intercept_R, slope_L, slope_R} per component
-                const uint32_t amp_addr = smem_u32(&sc.amp[k * ipv + s]);
-                // this pixel's row: the CTA's staged copy in shared memory when the vector belongs to
-                // the tile's pixel, else straight from HBM/L2
-                const bool staged = have_data && pix == pix0;
-                const uint32_t srow = staged ? smem_u32(sdata + s * a.n_pad) : 0u;   // 128-byte aligned
-                const char *grow = nullptr;
-                if (have_data) grow = reinterpret_cast<const char *>(a.data + pix * a.pix_stride + (int64_t)s * a.n_pad);
-                if (WRITE_PRED)       // chunks without lines stay zero; the others are overwritten by the same lane
-                    for (int j = lane; j < a.n_chan; j += 32) a.pred[(b * n_spec + s) * (int64_t)a.n_chan + j] = 0.0f;
-                float acc = 0.0f;
-                for (int sb = 0; sb < nchunks; sb += 32) {
-                    // ---- T: work list of the super-block, lanes <-> chunks ----
-                    int nseg;
-                    {
-                        if (sb > 0) {   // later super-blocks (n_chan > 2048): recount from the stored keys
-                            for (int idx = lane; idx < NC * 36; idx += 32) cw[idx] = 0u;
-                            __syncwarp();
-                            const int NL = sm.nlines, nitems = NC * NL;
-                            for (int t0 = 0; t0 < nitems; t0 += 32) {
-                                const int t = t0 + lane;
-                                if (t < nitems) {
-                                    int c = 0;
-                                    if (NC > 1) c += t >= NL;
-                                    if (NC > 2) c += t >= 2 * NL;
-                                    if (NC > 3) c += t >= 3 * NL;
-                                    const int i = t - c * NL;
-                                    const short2 ky = keys[c * nkey + i];
-                                    // (half-chunk flags are not kept with the keys: both halves count as touched)
-                                    atomicAdd(&cw[c * 36 + min(max((int)ky.x - sb, 0), 32)], 0x10001u);
-                                    atomicAdd(&cw[c * 36 + min(max((int)ky.y - sb, 0), 32)], 0x1000100u);
-                                }
-                            }
-                            __syncwarp();
-                        }
-                        uint32_t v[NC], vraw[NC], vnext[NC];
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            v[c] = vraw[c] = cw[c * 36 + lane];
-                            vnext[c] = cw[c * 36 + lane + 1];
-                        }
-                        __syncwarp();
-                        uint32_t ent[NC], half[NC];
-                        int n_mine = 0;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const uint32_t u = __shfl_up_sync(NF_FULL, v[c], o);
-                                if (lane >= o) v[c] += u;
-                            }
-                            // the lines touching chunk g are the run [#ended(g), #started(g)) of the sorted records
-                            const int end = (int)(v[c] & 0xffu), first = (int)((v[c] >> 8) & 0xffu);
-                            const int cnt = end - first;
-                            const uint32_t addr = pair_addr + (uint32_t)(((c * 2 + (first & 1)) * npair + (first >> 1)) * (int)sizeof(Nh3Pair));
-                            ent[c] = cnt > 0 ? (addr | ((uint32_t)((cnt + 1) >> 1) << 18)) : 0u;
-                            n_mine += cnt > 0;
-                            // which 32-channel halves of the chunk the run touches: a line that started in an earlier
-                            // chunk covers the first half, one that goes on into a later chunk the second half
-                            const int start_here = (int)(vraw[c] & 0xffu), end_next = first + (int)((vnext[c] >> 8) & 0xffu);
-                            const bool hitA = (end - start_here - first) > 0 || ((vraw[c] >> 16) & 0xffu) != 0u;
-                            const bool hitB = (end - end_next) > 0 || (vnext[c] >> 24) != 0u;
-                            half[c] = (hitA && !hitB) ? 0x20000000u : ((hitB && !hitA) ? 0x40000000u : 0u);
-                        }
-                        int incl = n_mine;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int u = __shfl_up_sync(NF_FULL, incl, o);
-                            if (lane >= o) incl += u;
-                        }
-                        nseg = __shfl_sync(NF_FULL, incl, 31);
-                        int at = incl - n_mine;
-                        const int g = sb + lane;
-                        const uint32_t xbits = __float_as_uint((float)(g << 6));
-                        int left = n_mine;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            if (ent[c] != 0u) {
-                                --left;
-                                sc.seg[at++] = make_uint4(ent[c], amp_addr + (uint32_t)(c * n_spec) * 16u,
-                                                          (srow + ((uint32_t)g << 8)) | half[c] | (left == 0 ? 0x80000000u : 0u), xbits);
-                            }
-                        }
-                        // a chunk no line touches contributes its sum of d^2 (kept per pixel in HBM)
-                        if (have_data && n_mine == 0 && g < nchunks) {
-                            const float2 q = __ldg(reinterpret_cast<const float2 *>(
-                                a.d2chunk + (pix * n_spec + s) * (int64_t)(a.n_pad >> 5)) + g);
-                            acc += q.x + q.y;
-                        }
-                        __syncwarp();
-                    }
-                    // ---- M: main loop over the (chunk, component) records of this super-block ----
-                    uint32_t sa = smem_u32(sc.seg);
-                    const uint32_t send = sa + (uint32_t)nseg * 16u;
-                    float ma = 0.0f, mb = 0.0f;
-#pragma unroll 1
-                    for (; sa != send; sa += 16u) {
-                        const float4 sgf = lds128(sa);
-                        const uint32_t sx = __float_as_uint(sgf.x), sz = __float_as_uint(sgf.z);
-                        const float xa = sgf.w + lane_f, xb = xa + 32.0f;
-                        const uint64_t xa2 = pack2(xa, xa), xb2 = pack2(xb, xb);
-                        uint32_t ra = sx & 0x3ffffu;
-                        const uint32_t rend = ra + (sx >> 18) * (uint32_t)sizeof(Nh3Pair);
-                        const float4 am = lds128(__float_as_uint(sgf.y));          // {i_L, i_R, s_L, s_R}
-                        float tpa = 0.0f, tpb = 0.0f;                // -log2(e) * tau at the lane's two channels
-                        if ((sz & 0x60000000u) == 0u) {
-                            // the run touches both 32-channel halves: two lines x two channels per trip (packed
-                            // FP32x2; a trailing odd slot holds the next line, whose own window test masks it off)
-#pragma unroll 1
-                            do {
-                                nh3_pair_term(tpa, tpb, ra, xa2, xb2);
-                                ra += (uint32_t)sizeof(Nh3Pair);
-                            } while (ra != rend);
-                        } else if (sz & 0x40000000u) {
-                            // the run touches the second half only: two lines x one channel per trip
-#pragma unroll 1
-                            do {
-                                nh3_pair_term1(tpb, ra, xb2);
-                                ra += (uint32_t)sizeof(Nh3Pair);
-                            } while (ra != rend);
-                        } else {
-#pragma unroll 1
-                            do {
-                                nh3_pair_term1(tpa, ra, xa2);
-                                ra += (uint32_t)sizeof(Nh3Pair);
-                            } while (ra != rend);
-                        }
-                        // 1 - exp(-tau): FastExp's Taylor branch below 2^-5 (fastexp.c:265-270); a half the run does
-                        // not touch has tp = 0 and contributes exactly 0
-                        const uint64_t tp2 = pack2(tpa, tpb);
-                        float e1sa, e1sb;
-                        unpack2(mul2(tp2, fma2(tp2, fma2(tp2, pack2(kC3, kC3), pack2(kC2, kC2)), pack2(kC1, kC1))), e1sa, e1sb);
-                        const float e1la = 1.0f - ex2_approx(tpa), e1lb = 1.0f - ex2_approx(tpb);
-                        const float e1a = tpa > kThr ? e1sa : e1la, e1b = tpb > kThr ? e1sb : e1lb;
-                        float aLa, aRa, aLb, aRb;
-                        unpack2(fma2(pack2(am.z, am.w), xa2, pack2(am.x, am.y)), aLa, aRa);
-                        unpack2(fma2(pack2(am.z, am.w), xb2, pack2(am.x, am.y)), aLb, aRb);
-                        ma = fmaf(fmaxf(aLa, aRa), e1a, ma);
-                        mb = fmaf(fmaxf(aLb, aRb), e1b, mb);
-                        if ((int)sz < 0) {                           // last component of this chunk: residual
-                            if (WRITE_PRED) {
-                                const int j = (int)xa;
-                                float *row = a.pred + (b * n_spec + s) * (int64_t)a.n_chan;
-                                if (j < a.n_chan) row[j] = ma;
-                                if (j + 32 < a.n_chan) row[j + 32] = mb;
-                            } else {
-                                // byte address of this lane's first channel: the row base is 128-byte aligned
-                                const uint32_t off = (sz & 0x3ffffu) | lane4;
-                                float da, db;
-                                if (staged) { da = lds_f32(off); db = lds_f32(off + 128u); }
-                                else {
-                                    da = __ldg(reinterpret_cast<const float *>(grow + off));
-                                    db = __ldg(reinterpret_cast<const float *>(grow + off + 128u));
-                                }
-                                const float ra_ = da - ma, rb_ = db - mb;
-                                acc = fmaf(ra_, ra_, acc);
-                                acc = fmaf(rb_, rb_, acc);
-                            }
-                            ma = 0.0f;
-                            mb = 0.0f;
-                        }
-                    }
-                }
-                if (have_data) {
-                    const double tot = warp_sum((double)acc);
-                    lnl -= tot * __ldg(a.inv2s2 + pix * n_spec + s);
-                }
-                __syncwarp();
-            }
-            if (a.lnL && lane == 0) a.lnL[b] = lnl;
-        }
-        __syncwarp();
-    }
-    // a CTA whose warps all ran out of vectors must still drain the bulk copy
-    if (!data_ready) mbar_wait(bar, 0);
-}
-
-// =================================================================================================
-// Block-owner layout.  The work unit of the main loop is one (component, 8-channel block) of a spectrum: a lane owns
-// the block, walks the hyperfine lines whose windows reach it (a contiguous run of the frequency-sorted records,
-// one 24-byte record fetch per line and block) and keeps the optical depth of its eight channels in registers; the
-// radiative transfer then runs on eight channels per lane with every lane busy.  The (component, block) items of a
-// super-block (1024 channels of one spectrum) are counting-sorted by the length of their run, so that the 32 items of
-// a round have about the same number of lines; within a class they keep the order (component, block mod 4, block / 4),
-// so the lanes of a round mostly share their line records (broadcast reads) and own blocks of ONE component.  The
-// model of the super-block is accumulated in shared memory and the residual is taken over all its channels, four per
-// lane.
-//
-//   tp_j = -log2(e) tau_j = sum_i mA_i 2^((B_i - k2_i d) d + L_i),  d = j - R'_i (exact),  |d| <= h_i
-//   with mA_i = -log2(e) tau_main w_i kept OUTSIDE the exponent (the exponent then vanishes at the line centre,
-//   where its rounding matters most), B_i = 2 k2 phi', L_i = -k2 phi'^2.
+// Why the items are sorted: the 32 items of a round run for as many trips as the longest of their runs, and runs
+// range from 1 line (the edge of an outer satellite) to a dozen (overlapping main groups).  Within a class the items
+// keep the order (component, lane, block), so the lanes of a round mostly read the same line records (broadcast)
+// and usually own blocks of one component; items of different components can own the same channels, in which
+// case the components of the round add to the model in turn.
+#ifndef BLK_MINCTA
+#define BLK_MINCTA 3
+#endif
+#ifndef BLK_GRP
+#define BLK_GRP 4               // neighbouring blocks of a lane that enter the item list together (4, 2 or 1)
+#endif
 #define BLK_SB 128              // blocks per super-block
 #define BLK_STRIDE 132          // counting-array stride per component (slot 128 = beyond the super-block)
 #define BLK_PLANE 528           // bytes per plane of the model array: 32 float4 entries + 16 bytes of skew
@@ -677,9 +267,10 @@ struct __align__(16) BlkScratch {
     // own blocks 4 l + q (accumulation) and lanes that read channels 128 i + 4 l ... (residual) both hit 8 different
     // 16-byte bank groups per quarter warp.
     float m[BLK_M_BYTES / 4];
-    uint32_t items[NC * BLK_SB + 32];     // sorted items: block | component << 7 | first line << 9 | lines << 15;
+    uint32_t items[NC * BLK_STRIDE];      // sorted items: block | component << 7 | first line << 9 | lines << 15;
                                           // doubles as the counting array cnt[NC][BLK_STRIDE] while the list is built
-    uint32_t hist[16], base[16];          // counting sort by run length: class 15 - min(lines, 15)
+    // (the 2 x 16 counters of the counting sort by run length -- class 15 - min(lines, 15) -- live in the skew words
+    // of the model planes: hist[k] in plane k / 4, base[k] in plane 4 + k / 4)
     float4 amp[32];                       // per set-up item: T_B amplitude as the max of two lines in j
     double soc[32], voc[32];              // sigma / c_kms, voff / c_kms
     float tauA[32];                       // log2(e) * tau_main
@@ -705,6 +296,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// the counters of the counting sort: four per plane, in the 16 skew bytes behind its 32 entries
+__device__ __forceinline__ uint32_t *blk_counter(float *m, int which, int k)
+{
+    return reinterpret_cast<uint32_t *>(m) + ((which * 4 + (k >> 2)) * BLK_PLANE + 512) / 4 + (k & 3);
+}
+
 // byte offset of the first half of block blk in the model array (second half: + BLK_PLANE)
 __device__ __forceinline__ uint32_t blk_m_off(int blk)
 {
@@ -715,20 +312,22 @@ __device__ __forceinline__ uint32_t blk_m_off(int blk)
 __device__ __forceinline__ void blk_m_add(uint32_t ma, const float (&val)[8])
 {
     float4 u = lds128(ma), v = lds128(ma + BLK_PLANE);
-    u.x += val[0]; u.y += val[1]; u.z += val[2]; u.w += val[3];
-    v.x += val[4]; v.y += val[5]; v.z += val[6]; v.w += val[7];
+    unpack2(add2(pack2(u.x, u.y), pack2(val[0], val[1])), u.x, u.y);
+    unpack2(add2(pack2(u.z, u.w), pack2(val[2], val[3])), u.z, u.w);
+    unpack2(add2(pack2(v.x, v.y), pack2(val[4], val[5])), v.x, v.y);
+    unpack2(add2(pack2(v.z, v.w), pack2(val[6], val[7])), v.z, v.w);
     sts128(ma, u);
     sts128(ma + BLK_PLANE, v);
 }
 
 template <int MODEL, int NC, bool WRITE_PRED, typename PT>
-__global__ void __launch_bounds__(NF_THREADS, 2)
-nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
+__global__ void __launch_bounds__(NF_THREADS, (NC <= 3 ? BLK_MINCTA : 2))
+nf_nh3_kernel(const __grid_constant__ NfLikeArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float *sdata = reinterpret_cast<float *>(smem_raw + 128);
-    const int data_floats = a.n_spec * a.n_pad;
+    const int data_floats = a.stage ? a.n_spec * a.n_pad : 0;      // the tile's pixel is staged unless it does not fit
     typedef BlkScratch<NC> Scratch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrec = a.npair;                              // records per component (lines of the widest transition; even)
@@ -749,15 +348,15 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
     const int64_t B = a.B_dev ? min(a.B, (int64_t)__ldg(a.B_dev)) : a.B;
     if (b0 >= B) return;
     constexpr bool have_data = !WRITE_PRED;
-    int64_t pix0 = 0;
-    if (have_data) {
+    int64_t pix0 = -1;
+    if (have_data && a.stage) {
         pix0 = a.pix_of_vec ? (int64_t)__ldg(a.pix_of_vec + b0) : b0 / a.vecs_per_pix;
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0)
             tma_load_1d(sdata, a.data + pix0 * a.pix_stride, (uint32_t)(data_floats * 4), bar);
     }
-    bool data_ready = !have_data;
+    bool data_ready = !(have_data && a.stage);
     for (int idx = lane; idx < BLK_M_BYTES / 4; idx += 32) sc.m[idx] = 0.0f;
 
     const int n_spec = a.n_spec;
@@ -871,7 +470,7 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         }
                         __syncwarp();
                     }
-                    if (lane < 16) sc.hist[lane] = 0u;
+                    if (lane < 16) *blk_counter(sc.m, 0, lane) = 0u;
                     // inclusive prefix of {lines started, lines ended} at the lane's blocks 4 lane .. 4 lane + 3:
                     // the lines reaching block g are the run [#ended(g), #started(g)) of the sorted records
                     uint32_t pre[NC][4];
@@ -889,48 +488,69 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         pre[c][0] = excl + s0; pre[c][1] = excl + s1; pre[c][2] = excl + s2; pre[c][3] = excl + s3;
                     }
                     __syncwarp();     // every lane has read its counts: the item list may overwrite them
-                    // class sizes (the hardware aggregates the lanes that add to one class)
+                    // The four blocks of a lane (one component) enter the list together, in the class of the longest
+                    // of their runs: neighbouring blocks have nearly the same lines, and one shared-memory atomic per
+                    // (component, lane) instead of four keeps the dependent chain of the placement short.
+                    constexpr int NG = 4 / BLK_GRP;      // groups of BLK_GRP neighbouring blocks per lane and component
+                    int qn[NC][NG], qk[NC][NG];          // items of the group, its class
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int n = (int)(pre[c][q] & 0xffu) - (int)((pre[c][q] >> 8) & 0xffu);
-                            if (n > 0) atomicAdd(&sc.hist[15 - min(n, 15)], 1u);
+                        for (int g = 0; g < NG; ++g) {
+                            int nmax = 0, cnt = 0;
+#pragma unroll
+                            for (int q = g * BLK_GRP; q < (g + 1) * BLK_GRP; ++q) {
+                                const int n = (int)(pre[c][q] & 0xffu) - (int)((pre[c][q] >> 8) & 0xffu);
+                                nmax = max(nmax, n);
+                                cnt += n > 0;
+                            }
+                            qn[c][g] = cnt;
+                            qk[c][g] = 15 - min(nmax, 15);
+                            if (cnt > 0) atomicAdd(blk_counter(sc.m, 0, qk[c][g]), (uint32_t)cnt);
                         }
                     __syncwarp();
                     int nit;
                     {
-                        const uint32_t hv = lane < 16 ? sc.hist[lane] : 0u;
+                        const uint32_t hv = lane < 16 ? *blk_counter(sc.m, 0, lane) : 0u;
                         uint32_t incl = hv;
 #pragma unroll
                         for (int o = 1; o < 16; o <<= 1) {
                             const uint32_t u = __shfl_up_sync(NF_FULL, incl, o);
                             if (lane >= o) incl += u;
                         }
-                        if (lane < 16) sc.base[lane] = incl - hv;
+                        if (lane < 16) *blk_counter(sc.m, 1, lane) = incl - hv;
                         nit = (int)__shfl_sync(NF_FULL, incl, 15);
                     }
                     __syncwarp();
-                    // placement: classes in descending run length; within a class the candidate slots follow one
-                    // another in the order (component, block mod 4)
+                    // placement: classes in descending run length; the blocks of a group stay together
+                    uint32_t qpos[NC][NG];
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int end = (int)(pre[c][q] & 0xffu), first = (int)((pre[c][q] >> 8) & 0xffu);
-                            const int n = end - first;
-                            if (n > 0) {
-                                const uint32_t pos = atomicAdd(&sc.base[15 - min(n, 15)], 1u);
-                                sc.items[pos] = (uint32_t)(4 * lane + q) | ((uint32_t)c << 7) | ((uint32_t)first << 9) |
-                                                ((uint32_t)n << 15);
+                        for (int g = 0; g < NG; ++g) {
+                            qpos[c][g] = 0u;
+                            if (qn[c][g] > 0) qpos[c][g] = atomicAdd(blk_counter(sc.m, 1, qk[c][g]), (uint32_t)qn[c][g]);
+                        }
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            uint32_t pos = qpos[c][g];
+#pragma unroll
+                            for (int q = g * BLK_GRP; q < (g + 1) * BLK_GRP; ++q) {
+                                const uint32_t first = (pre[c][q] >> 8) & 0xffu;
+                                const int n = (int)(pre[c][q] & 0xffu) - (int)first;
+                                if (n > 0) {
+                                    sc.items[pos] = (uint32_t)(4 * lane + q) | ((uint32_t)c << 7) | (first << 9) | ((uint32_t)n << 15);
+                                    ++pos;
+                                }
                             }
                         }
-                    if (nit + lane < ((nit + 31) & ~31)) sc.items[nit + lane] = 0u;   // idle lanes of the last round
                     __syncwarp();
 
                     // ---- M: rounds of 32 items ----
                     for (int r0 = 0; r0 < nit; r0 += 32) {
-                        const uint32_t item = sc.items[r0 + lane];
+                        const uint32_t item = r0 + lane < nit ? sc.items[r0 + lane] : 0u;   // idle lanes: no lines
                         const int n = (int)((item >> 15) & 63u), c = (int)((item >> 7) & 3u);
                         const int blk = (int)(item & 127u), first = (int)((item >> 9) & 63u);
                         const int T = __reduce_max_sync(NF_FULL, n);
@@ -980,15 +600,21 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
                         // accumulate into the model.  Items of ONE component own different blocks (the usual round);
                         // a round that holds several components adds them in turn
                         const uint32_t ma = m_addr + blk_m_off(blk);
-                        const int c_first = __shfl_sync(NF_FULL, c, 0);
-                        if (__all_sync(NF_FULL, n == 0 || c == c_first)) {
+                        if (NC == 1) {
                             if (n > 0) blk_m_add(ma, val);
                             __syncwarp();
                         } else {
-#pragma unroll
-                            for (int cc = 0; cc < NC; ++cc) {
-                                if (c == cc && n > 0) blk_m_add(ma, val);
+                            const int c_first = __shfl_sync(NF_FULL, c, 0);
+                            if (__all_sync(NF_FULL, n == 0 || c == c_first)) {
+                                if (n > 0) blk_m_add(ma, val);
                                 __syncwarp();
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc < NC; ++cc) {
+                                    if (!__any_sync(NF_FULL, c == cc && n > 0)) continue;
+                                    if (c == cc && n > 0) blk_m_add(ma, val);
+                                    __syncwarp();
+                                }
                             }
                         }
                     }
@@ -1055,38 +681,10 @@ nf_nh3_blk_kernel(const __grid_constant__ NfLikeArgs a)
 }
 
 template <int NC>
-static size_t nh3_blk_smem_bytes(const NfLikeArgs &a, int nwarps)
+static size_t nh3_smem_bytes(const NfLikeArgs &a, int nwarps)
 {
-    const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
+    const size_t data = a.stage ? (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128 : 0;
     return 128 + data + ((size_t)NC * a.npair * 24 + (size_t)NC * a.nkey * sizeof(short2) + sizeof(BlkScratch<NC>)) * nwarps;
-}
-
-template <int MODEL, int NC, bool WP, typename PT>
-static cudaError_t nh3_blk_launch_one(const NfLikeArgs &a0, cudaStream_t st)
-{
-    NfLikeArgs a = a0;
-    int max_lines = 1;
-    for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
-    a.npair = (max_lines + 1) & ~1;                            // records per component (even: 16-byte aligned arrays)
-    a.nkey = a.n_chan > BLK_SB * 8 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
-    auto kern = nf_nh3_blk_kernel<MODEL, NC, WP, PT>;
-    const size_t smem = nh3_blk_smem_bytes<NC>(a, NH3_WARPS);
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = nf_ensure_dyn_smem((const void *)kern, smem);
-    if (e) return e;
-    const int tile = a.tile_vecs > 0 ? a.tile_vecs : NF_TILE_VECS;
-    const int64_t grid = (a.B + tile - 1) / tile;
-    if (grid <= 0) return cudaSuccess;
-    kern<<<(unsigned)grid, NF_THREADS, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-template <int NC>
-static size_t nh3_smem_bytes(const NfLikeArgs &a)
-{
-    const size_t data = (((size_t)a.n_spec * a.n_pad * 4 + 127) / 128) * 128;
-    return 128 + data + ((size_t)NC * 2 * a.npair * sizeof(Nh3Pair) + (size_t)NC * a.nkey * sizeof(short2) +
-                         sizeof(Nh3Scratch<NC>)) * NH3_WARPS;
 }
 
 template <int MODEL, int NC, bool WP, typename PT>
@@ -1095,10 +693,16 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     NfLikeArgs a = a0;
     int max_lines = 1;
     for (int s = 0; s < a.n_spec; ++s) max_lines = a.spec[s].nlines > max_lines ? a.spec[s].nlines : max_lines;
-    a.npair = (max_lines >> 1) + 1;     // lines 0..NL (NL = the null line) in pairs of either parity
-    a.nkey = a.n_chan > 2048 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
+    a.npair = (max_lines + 1) & ~1;                            // records per component (even: 16-byte aligned arrays)
+    a.nkey = a.n_chan > BLK_SB * 8 ? ((max_lines + 3) & ~3) : 0;   // line keys are only re-read by later super-blocks
     auto kern = nf_nh3_kernel<MODEL, NC, WP, PT>;
-    const size_t smem = nh3_smem_bytes<NC>(a);
+    // the tile's pixel is staged in shared memory by one bulk copy; rows too long for that are read from HBM / L2
+    a.stage = WP ? 0 : 1;
+    size_t smem = nh3_smem_bytes<NC>(a, NH3_WARPS);
+    if (smem > 227 * 1024 && a.stage) {
+        a.stage = 0;
+        smem = nh3_smem_bytes<NC>(a, NH3_WARPS);
+    }
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = nf_ensure_dyn_smem((const void *)kern, smem);
     if (e) return e;
@@ -1109,21 +713,10 @@ static cudaError_t nh3_launch_one(const NfLikeArgs &a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
-static bool nh3_use_v8()
-{
-    static const bool v8 = [] { const char *e = getenv("NF_NH3_KERNEL"); return e && e[0] == 'v'; }();
-    return v8;
-}
-
 template <int MODEL, int NC>
 static cudaError_t nh3_launch_nc(const NfLikeArgs &a, cudaStream_t st)
 {
     const bool wp = a.pred != nullptr;
-    if (!nh3_use_v8()) {
-        if (a.param_f64)
-            return wp ? nh3_blk_launch_one<MODEL, NC, true, double>(a, st) : nh3_blk_launch_one<MODEL, NC, false, double>(a, st);
-        return wp ? nh3_blk_launch_one<MODEL, NC, true, float>(a, st) : nh3_blk_launch_one<MODEL, NC, false, float>(a, st);
-    }
     if (a.param_f64)
         return wp ? nh3_launch_one<MODEL, NC, true, double>(a, st) : nh3_launch_one<MODEL, NC, false, double>(a, st);
     return wp ? nh3_launch_one<MODEL, NC, true, float>(a, st) : nh3_launch_one<MODEL, NC, false, float>(a, st);
