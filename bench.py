@@ -367,9 +367,10 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(P32.nbytes),
                 "d2h_bytes_per_step": int(B_TOTAL * 8), "steps": n_e2e,
-                "api": "nf_nh3_loglike_host (pinned host buffers, 2-stream pipelined chunks)",
+                "api": "nf_nh3_loglike_host (pinned host buffers, chunks pipelined over a ring of 3 streams)",
                 "pageable_host_buffers": {"value": evals * n_e2e / e2e_pg_s, "unit": "evals/s",
-                                          "note": "same call, plain numpy arrays (what a reference-side caller passes)"}},
+                                          "note": "same call, plain numpy arrays (what a reference-side caller passes): bounced through the "
+                                                  "library's page-locked ring by 4 host threads"}},
         "gpu_launches": args.steps,
         "roofline": roofline,
     }

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <map>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -136,12 +137,15 @@ int pixels_alloc(int device, int model, int64_t n_pix, int n_spec, int n_chan, c
     if ((e = cudaMalloc(&px->data, nrow * px->n_pad * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&px->inv2s2, nrow * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&px->null_lnz, (size_t)n_pix * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&px->d2chunk, nrow * (px->n_pad / 32) * sizeof(float))) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&px->streams[0], cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&px->streams[1], cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaMalloc(&px->d2chunk, nrow * (px->n_pad / 32) * sizeof(float))) != cudaSuccess) {
         nf_pixels_free(px);
         return (int)e;
     }
+    for (int i = 0; i < NF_HOST_SLOTS; ++i)
+        if ((e = cudaStreamCreateWithFlags(&px->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
+            nf_pixels_free(px);
+            return (int)e;
+        }
     *out = px;
     return NF_OK;
 }
@@ -171,14 +175,65 @@ int ensure_stage(const nf_pixels *cpx, size_t bytes)
 {
     nf_pixels *px = const_cast<nf_pixels *>(cpx);
     if (px->stage_bytes >= bytes) return NF_OK;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) {
         if (px->stage_dev[i]) cudaFree(px->stage_dev[i]);
         px->stage_dev[i] = nullptr;
     }
     px->stage_bytes = 0;
-    for (int i = 0; i < 2; ++i) NF_CUDA(cudaMalloc(&px->stage_dev[i], bytes));
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) NF_CUDA(cudaMalloc(&px->stage_dev[i], bytes));
     px->stage_bytes = bytes;
     return NF_OK;
+}
+
+// Page-locked twin of the device staging buffers, for callers that hand over pageable memory (plain numpy arrays).
+int ensure_stage_host(const nf_pixels *cpx, size_t bytes)
+{
+    nf_pixels *px = const_cast<nf_pixels *>(cpx);
+    if (px->stage_host_bytes >= bytes) return NF_OK;
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) {
+        if (px->stage_host[i]) cudaFreeHost(px->stage_host[i]);
+        px->stage_host[i] = nullptr;
+    }
+    px->stage_host_bytes = 0;
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) NF_CUDA(cudaHostAlloc(&px->stage_host[i], bytes, cudaHostAllocDefault));
+    px->stage_host_bytes = bytes;
+    return NF_OK;
+}
+
+// true when the driver can DMA straight from / into the buffer (page-locked, registered or managed memory)
+bool host_ptr_is_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// host copy between a pageable buffer and the page-locked ring: a few threads, one thread cannot feed the kernel
+void host_copy(void *dst, const void *src, size_t bytes)
+{
+    const size_t part_min = (size_t)1 << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (bytes / part_min < nt) nt = bytes / part_min;
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (size_t i = 1; i < nt; ++i) {
+        const size_t o = i * part;
+        if (o >= bytes) break;
+        const size_t n = bytes - o < part ? bytes - o : part;
+        th.emplace_back([=] { std::memcpy((unsigned char *)dst + o, (const unsigned char *)src + o, n); });
+    }
+    std::memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto &t : th) t.join();
 }
 
 int make_args(const nf_pixels *px, const void *params, int param_dtype, const int32_t *pix_of_vec,
@@ -221,8 +276,12 @@ int run_device(const nf_pixels *px, const NfLikeArgs &a, void *stream)
     return (int)launch_model(px->model, a, st);
 }
 
-// Host-buffer call: chunks of vectors ping-pong over two streams so the H2D
+// Host-buffer call: chunks of vectors rotate over a ring of streams and staging buffers so the H2D
 // copy of chunk k+1 overlaps the kernel of chunk k and the D2H of chunk k-1.
+// Page-locked caller buffers are copied from / into directly.  Pageable ones (plain numpy arrays: what a
+// reference-side caller hands over) would serialise the pipeline -- a device-to-host copy into pageable memory
+// returns only when the kernel before it has finished -- so the log-likelihood call bounces them through a
+// page-locked ring: the host copies chunk k+1 into the ring while the kernel of chunk k runs.
 int run_host(const nf_pixels *px, int model, const void *params_host, int param_dtype,
              const int32_t *pix_host, int64_t vecs_per_pix, int64_t B, int ncomp, int flags,
              double *lnL_host, float *pred_host)
@@ -253,36 +312,58 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
     std::lock_guard<std::mutex> host_lock(*px->host_mu);
     int rc = ensure_stage(px, total);
     if (rc != NF_OK) return rc;
+    const bool bounce = !want_pred && (!host_ptr_is_pinned(params_host) || !host_ptr_is_pinned(pix_host) ||
+                                       !host_ptr_is_pinned(lnL_host));
+    if (bounce && (rc = ensure_stage_host(px, off_pred)) != NF_OK) return rc;
 
-    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
+    constexpr int S = NF_HOST_SLOTS;
+    cudaEvent_t ev0[S] = {}, ev1[S] = {};
     double kernel_ms = 0.0;
     int64_t launches = 0;
-    bool pending[2] = {false, false};
+    bool pending[S] = {};
+    int64_t pend_b0[S] = {}, pend_nb[S] = {};
     int status = NF_OK;
+    // the slot's previous chunk has drained its buffers: account its kernel time, hand its results over
+    auto drain = [&](int slot) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0[slot], ev1[slot]);
+        kernel_ms += ms;
+        if (bounce && lnL_host)
+            std::memcpy(lnL_host + pend_b0[slot], (const unsigned char *)px->stage_host[slot] + off_lnl,
+                        (size_t)pend_nb[slot] * 8);
+        pending[slot] = false;
+    };
     // errors inside the pipeline leave through `status` so that the events are always destroyed
 #define NF_STEP(expr) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { status = (int)e__; break; } }
-    for (int i = 0; i < 2 && status == NF_OK; ++i) {
+    for (int i = 0; i < NF_HOST_SLOTS && status == NF_OK; ++i) {
         NF_STEP(cudaEventCreate(&ev0[i]));
         NF_STEP(cudaEventCreate(&ev1[i]));
     }
     int64_t k = 0;
     for (int64_t b0 = 0; b0 < B && status == NF_OK; b0 += chunk, ++k) {
-        const int slot = (int)(k & 1);
+        const int slot = (int)(k % S);
         cudaStream_t st = px->streams[slot];
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
-        if (pending[slot]) {   // the slot's previous chunk must have drained its buffers
+        if (pending[slot]) {
             NF_STEP(cudaStreamSynchronize(st));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev0[slot], ev1[slot]);
-            kernel_ms += ms;
-            pending[slot] = false;
+            drain(slot);
         }
         unsigned char *dev = (unsigned char *)px->stage_dev[slot];
-        NF_STEP(cudaMemcpyAsync(dev, (const unsigned char *)params_host + (size_t)b0 * ndim * psz,
-                                (size_t)nb * ndim * psz, cudaMemcpyHostToDevice, st));
+        unsigned char *ring = bounce ? (unsigned char *)px->stage_host[slot] : nullptr;
+        const unsigned char *p_src = (const unsigned char *)params_host + (size_t)b0 * ndim * psz;
+        if (bounce) {
+            host_copy(ring, p_src, (size_t)nb * ndim * psz);
+            p_src = ring;
+        }
+        NF_STEP(cudaMemcpyAsync(dev, p_src, (size_t)nb * ndim * psz, cudaMemcpyHostToDevice, st));
         const int32_t *pix_dev = nullptr;
         if (pix_host) {
-            NF_STEP(cudaMemcpyAsync(dev + off_pix, pix_host + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+            const void *x_src = pix_host + b0;
+            if (bounce) {
+                std::memcpy(ring + off_pix, x_src, (size_t)nb * 4);
+                x_src = ring + off_pix;
+            }
+            NF_STEP(cudaMemcpyAsync(dev + off_pix, x_src, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
             pix_dev = (const int32_t *)(dev + off_pix);
         }
         NfLikeArgs a;
@@ -301,23 +382,24 @@ int run_host(const nf_pixels *px, int model, const void *params_host, int param_
         NF_STEP(cudaEventRecord(ev1[slot], st));
         ++launches;
         pending[slot] = true;
+        pend_b0[slot] = b0;
+        pend_nb[slot] = nb;
         if (lnL_host)
-            NF_STEP(cudaMemcpyAsync(lnL_host + b0, dev + off_lnl, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+            NF_STEP(cudaMemcpyAsync(bounce ? (void *)(ring + off_lnl) : (void *)(lnL_host + b0), dev + off_lnl,
+                                    (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
         if (want_pred)
             NF_STEP(cudaMemcpyAsync((unsigned char *)pred_host + (size_t)b0 * pred_per_vec, dev + off_pred,
                                     (size_t)nb * pred_per_vec, cudaMemcpyDeviceToHost, st));
     }
 #undef NF_STEP
-    for (int slot = 0; slot < 2; ++slot) {
+    // the chunks still in flight, oldest first
+    for (int i = 0; i < S; ++i) {
+        const int slot = (int)((k + i) % S);
         cudaError_t e = cudaStreamSynchronize(px->streams[slot]);
         if (e != cudaSuccess && status == NF_OK) status = (int)e;
-        if (pending[slot] && e == cudaSuccess) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev0[slot], ev1[slot]);
-            kernel_ms += ms;
-        }
+        if (pending[slot] && e == cudaSuccess) drain(slot);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) {
         if (ev0[i]) cudaEventDestroy(ev0[i]);
         if (ev1[i]) cudaEventDestroy(ev1[i]);
     }
@@ -431,8 +513,9 @@ int nf_pixels_free(nf_pixels *px)
     if (px->inv2s2) cudaFree(px->inv2s2);
     if (px->null_lnz) cudaFree(px->null_lnz);
     if (px->d2chunk) cudaFree(px->d2chunk);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NF_HOST_SLOTS; ++i) {
         if (px->stage_dev[i]) cudaFree(px->stage_dev[i]);
+        if (px->stage_host[i]) cudaFreeHost(px->stage_host[i]);
         if (px->streams[i]) cudaStreamDestroy(px->streams[i]);
     }
     delete px->host_mu;

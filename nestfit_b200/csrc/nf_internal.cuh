@@ -42,6 +42,8 @@ struct NfSpecMeta {
     int para;           // para (K % 3 != 0) or ortho
 };
 
+#define NF_HOST_SLOTS 3         // chunks in flight in a host-buffer call (ring of streams and staging buffers)
+
 struct nf_pixels {
     int device;
     int model;
@@ -54,10 +56,10 @@ struct nf_pixels {
     NfSpecMeta spec[NF_MAX_SPEC];
     // pipelined host-call resources (one host-buffer call at a time per block: guarded by host_mu)
     std::mutex *host_mu;
-    cudaStream_t streams[2];
-    void *stage_dev[2];
-    void *stage_host[2];
-    size_t stage_bytes;
+    cudaStream_t streams[NF_HOST_SLOTS];
+    void *stage_dev[NF_HOST_SLOTS];
+    void *stage_host[NF_HOST_SLOTS];            // page-locked twins of stage_dev, allocated on the first call with pageable buffers
+    size_t stage_bytes, stage_host_bytes;
 };
 
 struct nf_priors {
