@@ -130,7 +130,11 @@ int nf_gauss_predict(const nf_pixels *px, const void *params_dev, int param_dtyp
 /* ---- host-buffer entry points (the call a reference-side binding makes) -- */
 /* params_host [B][ndim] of param_dtype, pix_of_vec_host may be NULL (then
  * vecs_per_pix is used), lnL_host double[B].  Copies are pipelined with the
- * kernel over internal streams; the call returns when lnL_host is complete. */
+ * kernel over internal streams; the call returns when lnL_host is complete.
+ * Page-locked (cudaHostAlloc / cudaHostRegister) buffers are copied from and
+ * into directly; pageable ones (plain numpy arrays) are bounced through a
+ * page-locked ring owned by the block, so they are safe to pass and cost one
+ * extra host copy that overlaps the kernel. */
 int nf_nh3_loglike_host(const nf_pixels *px, const void *params_host, int param_dtype,
                         const int32_t *pix_of_vec_host, int64_t vecs_per_pix,
                         int64_t B, int ncomp, int flags, double *lnL_host);

@@ -276,8 +276,9 @@ def test_lnz_scatter_and_bias_three_components(nb):
     active, the pixel of the sampler study (tools/ns_study/harness.py: make_pixel(3, 103), 2 x 380 channels), fitted
     32 times in one batch with the cube fitter's settings (nlive 300, tol 1, default proposal scheme).  Asserted:
     the seed-to-seed scatter of ln Z against the error the runs report, and the mean against the long-walk value of
-    the study (-413.87 +- 0.14, walks of 140 steps on the CPU port, tools/ns_study/results.txt) -- the default scheme
-    is known to sit +1.3 above it; the test keeps both numbers from getting worse."""
+    the study (-413.87 +- 0.14, walks of 140 steps on the CPU port, tools/ns_study/results.txt), above which the
+    default scheme is known to sit.  Measured on B200: ln Z -413.02 +- 0.30 over the 32 runs,
+    reported error 0.375 (ratio 0.81), bias +0.85, 6.8e5 likelihood calls per run."""
     from nestfit_b200.sampler import NestedSamplingBatch
     rng = np.random.default_rng(103)
     ut = nb.get_irdc_priors()
@@ -299,5 +300,5 @@ def test_lnz_scatter_and_bias_three_components(nb):
     sd, ratio, bias = lnz.std(ddof=1), lnz.std(ddof=1) / err.mean(), lnz.mean() + 413.87
     print(f"3 components, 32 runs: ln Z {lnz.mean():.3f} +- {sd:.3f} (reported error {err.mean():.3f}, ratio {ratio:.2f}), "
           f"bias against the long-walk value {bias:+.2f}, evals per run {res['n_evals'].mean():.3g}")
-    assert ratio < 2.5, (sd, err.mean())
-    assert -1.0 < bias < 2.5, (lnz.mean(), bias)
+    assert ratio < 1.3, (sd, err.mean())
+    assert -0.5 < bias < 2.0, (lnz.mean(), bias)
