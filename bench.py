@@ -486,7 +486,7 @@ def _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag):
 
 
 def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, tag, blocks_per_gpu, posteriors=True,
-              concurrent_blocks=2):
+              concurrent_blocks=2, n_streams=1, pixels_per_stream=1024):
     """One cube-fit leg through the public API: `CubeFitter.fit_cube` at N = 1, its SPMD form `fit_cube_rank` (one
     existing process per GPU, blocks claimed dynamically, one store chunk per rank) at N > 1.  The timed region
     holds everything the call does: store creation, uploads, the fit, the posterior products, the chunk writes."""
@@ -496,7 +496,8 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
     stack, ut, ncomp_map, shm = _shared_cube(nb, shape, ncomp_max, noise_grad, seed, dev, rank, dist, tag)
     fitter = nb.CubeFitter(stack, ut, ammonia.AmmoniaRunner, ncomp_max=ncomp_max, lnZ_thresh=11,
                            mn_kwargs={'nlive': 100, 'tol': 1.0, 'efr': 0.3}, nlive_snr_fact=5, n_prop=32,
-                           store_posteriors=posteriors)
+                           store_posteriors=posteriors, n_streams=n_streams if world == 1 else 1,
+                           pixels_per_stream=pixels_per_stream)
     store_root = Path(os.environ.get("NF_BENCH_STORE", "/tmp")) / f"nf_bench_store_{os.environ.get('MASTER_PORT', '0')}_{tag}"
     if rank == 0:
         shutil.rmtree(store_root, ignore_errors=True)
@@ -545,7 +546,8 @@ def _cube_leg(nb, shape, ncomp_max, noise_grad, seed, rank, world, dev, dist, ta
         out = {"value": n_pix / wall, "unit": "pixels/s", "seconds": wall, "cube": [shape[0], shape[1], 2, N_CHAN],
                "ncomp_max": ncomp_max, "noise": "0.05..0.3 K gradient (NoiseMap)" if noise_grad else "0.1 K uniform",
                "nlive": "100 + 5*SNR", "tol": 1.0, "lnZ_thresh": 11, "blocks_per_gpu": blocks_per_gpu if world > 1 else 1,
-               "api": "CubeFitter.fit_cube(store, nproc=1)" if world == 1 else
+               "api": f"CubeFitter(n_streams={n_streams}, pixels_per_stream={pixels_per_stream}).fit_cube(store, nproc=1)"
+                      if world == 1 else
                       f"CubeFitter.fit_cube_rank(store, rank, {world}, blocks_per_gpu={blocks_per_gpu}, "
                       f"concurrent_blocks={concurrent_blocks})",
                "likelihood_evals_per_pixel": sum(p["n_evals"] for p in per_rank) / n_pix,
@@ -574,7 +576,8 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
     legs = {}
     sx, sy = (int(v) for v in args.scale_cube.lower().split("x"))
     if world == 1 and args.cube_size > 0:
-        out, aux = _cube_leg(nb, (args.cube_size, args.cube_size), 3, False, 77, rank, world, dev, dist, "c2", 1)
+        out, aux = _cube_leg(nb, (args.cube_size, args.cube_size), 3, False, 77, rank, world, dev, dist, "c2", 1,
+                             n_streams=args.cube_streams, pixels_per_stream=args.cube_pps)
         if rank == 0:
             out["metric"] = "cube pixels/s fit (configs[2]: ncomp 1-3 evidence model selection, 1 GPU)"
             out["scaling"] = "n/a (single GPU)"
@@ -583,7 +586,8 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
             legs["cube_fit_config2"] = out
     if sx > 0:
         out, _ = _cube_leg(nb, (sx, sy), 4, True, 78, rank, world, dev, dist, "c3", args.blocks_per_gpu,
-                           concurrent_blocks=args.concurrent_blocks)
+                           concurrent_blocks=args.concurrent_blocks, n_streams=args.cube_streams,
+                           pixels_per_stream=args.cube_pps)
         if rank == 0:
             out["metric"] = "cube pixels/s fit (configs[3] shape: ncomp <= 4, noise map; one fixed cube over N GPUs)"
             out["scaling"] = "strong"
@@ -592,7 +596,8 @@ def run_cube_fit(nb, args, rank, world, dev, dist):
         # the posterior rows of 262 144 pixels are ~400 GB: this leg stores everything but them (attributes,
         # marginals, best-fit / MAP vectors); the two smaller legs store the posteriors as well
         out, _ = _cube_leg(nb, (512, 512), 4, True, 79, rank, world, dev, dist, "c3full", args.blocks_per_gpu,
-                           posteriors=False, concurrent_blocks=args.concurrent_blocks)
+                           posteriors=False, concurrent_blocks=args.concurrent_blocks, n_streams=args.cube_streams,
+                           pixels_per_stream=args.cube_pps)
         if rank == 0:
             out["metric"] = "cube pixels/s fit (configs[3]: 512x512, ncomp <= 4, noise map)"
             out["scaling"] = "strong"
@@ -789,6 +794,9 @@ def main():
     ap.add_argument("--scale-cube", default="256x128",
                     help="LONxLAT of the fixed configs[3]-shaped cube fitted at every N (strong scaling; 0x0 = skip)")
     ap.add_argument("--full-cube", action="store_true", help="also fit the full 512x512 configs[3] cube (default at N = 8)")
+    ap.add_argument("--cube-streams", type=int, default=1,
+                    help="N = 1 cube legs: host threads / CUDA streams that escalate sub-blocks of a wave concurrently")
+    ap.add_argument("--cube-pps", type=int, default=1024, help="pixels per sub-block when --cube-streams > 1")
     ap.add_argument("--blocks-per-gpu", type=int, default=8, help="over-decomposition of the multi-GPU cube fit")
     ap.add_argument("--concurrent-blocks", type=int, default=2,
                     help="groups of blocks a rank keeps in flight (host threads / streams)")
