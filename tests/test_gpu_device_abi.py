@@ -91,3 +91,50 @@ def test_device_pointer_entry_points(nb):
     # error paths: wrong model for the entry point, ncomp too large
     assert lib.nf_nh3_loglike(bg.handle, _p(d_p), _lib.NF_F64, None, 1, B, 1, 0, _p(d_l), None) == -1
     assert lib.nf_n2hp_loglike(bn.handle, _p(d_p), _lib.NF_F64, None, 1, B, 5, _p(d_l), None) == -1
+
+
+def test_host_call_pageable_and_pinned_buffers_agree(nb):
+    """The host-buffer call takes page-locked buffers directly and bounces pageable ones (plain numpy arrays) through
+    its own page-locked ring (csrc/nf_capi.cu: run_host): both give the device call's lnL bit for bit, over several
+    131 072-vector chunks with a ragged last one, with the implicit and with an explicit vector -> pixel map, and
+    with the three arguments pinned in any combination."""
+    import torch
+    from nestfit_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    ut = nb.get_irdc_priors()
+    n_pix, n_chan, ncomp, vpp = 37, 128, 1, 8192
+    B = n_pix * vpp - 1000                     # 2.3 chunks; the last pixel is short of vectors
+    xs = [orc.bench_axis(1, n_chan, 0.4), orc.bench_axis(2, n_chan, 0.4)]
+    data = rng.normal(0, 0.1, (n_pix, 2, n_chan)).astype(np.float32)
+    blk = nb.PixelBlock("ammonia", xs, data, 0.1, trans_ids=[1, 2])
+    P = ut.transform_batch(rng.uniform(size=(B, 6)), ncomp)
+    P[~np.isfinite(P).all(axis=1)] = P[np.isfinite(P).all(axis=1)][0]
+    P = np.ascontiguousarray(P.astype(np.float32))
+    pix = (np.arange(B) // vpp).astype(np.int32)
+    # the device call is the reference
+    d_p, d_x = torch.from_numpy(P).cuda(), torch.from_numpy(pix).cuda()
+    d_l = torch.empty(B, dtype=torch.float64, device="cuda")
+    _lib.check(lib.nf_nh3_loglike(blk.handle, _p(d_p), _lib.NF_F32, None, vpp, B, ncomp, 0, _p(d_l), None), "device call")
+    torch.cuda.synchronize()
+    want = d_l.cpu().numpy()
+    assert np.isfinite(want).all()
+
+    def pinned(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        assert t.is_pinned()
+        return t
+
+    tp, tx, tl = pinned(P), pinned(pix), torch.empty(B, dtype=torch.float64).pin_memory()
+    for pin_p, pin_x, pin_l in ((0, 0, 0), (1, 1, 1), (1, 0, 0), (0, 1, 1), (0, 0, 1)):
+        for explicit in (False, True):
+            out = np.full(B, np.nan)
+            tl.fill_(float("nan"))
+            a_p = C.c_void_p(tp.data_ptr()) if pin_p else _lib.ptr(P)
+            a_x = None if not explicit else (C.c_void_p(tx.data_ptr()) if pin_x else _lib.ptr(pix))
+            a_l = C.c_void_p(tl.data_ptr()) if pin_l else _lib.ptr(out)
+            _lib.check(lib.nf_nh3_loglike_host(blk.handle, a_p, _lib.NF_F32, a_x, 0 if explicit else vpp, B, ncomp, 0, a_l),
+                       "host call")
+            got = tl.numpy() if pin_l else out
+            np.testing.assert_array_equal(got, want)
+    blk.close()
