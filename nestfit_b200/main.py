@@ -688,10 +688,10 @@ class CubeFitter:
                     th.join()
         finally:
             sink.close()
+        self.stats['rank_fit_seconds'] = time.perf_counter() - t0
+        barrier()           # reached by a failing rank too: the others wait here, and must not wait for ever
         if errors:
             raise errors[0]
-        self.stats['rank_fit_seconds'] = time.perf_counter() - t0
-        barrier()
         if rank == 0:
             with HdfStore(store_name) as store:
                 store.link_files()

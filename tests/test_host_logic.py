@@ -337,6 +337,41 @@ def test_fit_cube_rank_spmd_claims(tmp_path, monkeypatch, nb):
     store.close()
 
 
+def test_fit_cube_rank_failing_rank_reaches_the_barrier(tmp_path, monkeypatch, nb):
+    """A rank whose block fit raises still arrives at the barrier that follows the fit (the other ranks of a torchrun
+    job would otherwise hang in it) and raises afterwards; the healthy ranks return."""
+    import importlib
+    import threading
+    from nestfit_b200.models import ammonia
+    (tmp_path / 'nf_stubfit3.py').write_text(STUB_FITTER)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    stub = importlib.import_module('nf_stubfit3')
+    world = 2
+    bar = threading.Barrier(world, timeout=60)
+    out, errs = {}, {}
+
+    class Failing(stub.StubFitter):
+        def fit_block(self, indices, device=0, group_root=None, verbose=False):
+            if device == 1:
+                raise RuntimeError('device 1 is on fire')
+            return super().fit_block(indices, device=device, group_root=group_root, verbose=verbose)
+
+    def rank_main(r):
+        try:
+            fitter = Failing(stub.StubStack(), None, ammonia.AmmoniaRunner, ncomp_max=1)
+            out[r] = fitter.fit_cube_rank(str(tmp_path / 'spmd_fail'), r, world, blocks_per_gpu=2, device=r, barrier=bar.wait)
+        except BaseException as exc:
+            errs[r] = exc
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in threads)
+    assert 0 in out and list(errs) == [1] and 'on fire' in str(errs[1])       # no BrokenBarrierError anywhere
+
+
 def test_slab_store_wave_round_trip(tmp_path, nb):
     """A finished wave (posterior pool + run offsets + attribute columns) written as a slab and read back through
     the reference's tree: /pix/<lon>/<lat>/<ncomp> groups with the dumper's attributes and datasets, lazily
